@@ -1,0 +1,323 @@
+"""The batch-parallel adaptive solve loop (API of torchode/adjoints.py:26-319).
+
+``AutoDiffAdjoint.solve`` keeps the reference's signature and Solution, and picks one of
+three routes:
+
+* **fused** (path B) -- built-in step method + built-in controller + built-in analytic
+  field: the whole solve is ONE kernel launch (``tode_solve_fused``).
+* **staged** (path A) -- built-in step method + controller around an opaque user ``f``:
+  per iteration 6 stage kernels interleaved with the 6 calls of ``f`` and one finish
+  kernel; the host never synchronises inside an iteration, it polls a device control
+  block a few iterations late.
+* **generic** -- any foreign ``SingleStepMethod`` / ``StepSizeController`` plug-in object
+  (the reference's operator API, e.g. the stubs of its test-suite): the loop bookkeeping
+  is orchestrated from Python exactly like adjoints.py:135-260 and calls the plug-ins'
+  protocol methods.
+
+There is no CPU route for the built-in components: CPU tensors raise.
+"""
+import ctypes as C
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _cabi, _launch, status_codes
+from .fields import BuiltinField
+from .problems import InitialValueProblem
+from .single_step_methods import Dopri5, SingleStepMethod, Tsit5
+from .solution import Solution
+from .step_size_controllers import IntegralController, PIDController, StepSizeController
+from .terms import ODETerm
+
+_INT32_MAX = 2**31 - 1
+
+
+class AutoDiffAdjoint(nn.Module):
+    def __init__(self, step_method: SingleStepMethod, step_size_controller: StepSizeController, *,
+                 max_steps: Optional[int] = None, backprop_through_step_size_control: bool = True):
+        super().__init__()
+        self.step_method = step_method
+        self.step_size_controller = step_size_controller
+        self.max_steps = max_steps
+        self.backprop_through_step_size_control = backprop_through_step_size_control
+        #: how many loop iterations the host may run ahead of the device (staged route)
+        self.lookahead = 3
+
+    # ------------------------------------------------------------------------------------
+    def _kernel_route(self) -> bool:
+        """Built-in components whose arithmetic the CUDA kernels implement."""
+        return (type(self.step_method) in (Dopri5, Tsit5) and self.step_method.fusable()
+                and type(self.step_size_controller) in (IntegralController, PIDController)
+                and self.step_size_controller.fusable())
+
+    def solve(self, problem: InitialValueProblem, term: Optional[ODETerm] = None,
+              dt0: Optional[torch.Tensor] = None, args: Any = None) -> Solution:
+        if term is None:
+            term_ = self.step_method.term
+            assert term_ is not None, "pass the ODE term to solve() or to the step method"
+        else:
+            term_ = term
+        if not self._kernel_route():
+            return self._solve_generic(problem, term, term_, dt0, args)
+
+        _launch.require_cuda(problem.y0, problem.t_start, problem.t_end, problem.t_eval, dt0)
+        if torch.is_grad_enabled() and (
+                problem.y0.requires_grad or any(p.requires_grad for p in term_.parameters())):
+            raise NotImplementedError(
+                "the CUDA solve loop is forward-only: wrap the call in torch.no_grad() (autograd "
+                "through the fused kernels is not implemented yet)")
+        with torch.no_grad(), torch.cuda.device(problem.device):
+            f = term_.f
+            if (isinstance(f, BuiltinField) and not term_.with_args and problem.n_features <= 4
+                    and (f.n_features is None or f.n_features == problem.n_features)):
+                sol = self._solve_fused(problem, term_, f, dt0)
+                if sol is not None:
+                    return sol
+            return self._solve_staged(problem, term_, dt0, args)
+
+    # ------------------------------------------------------------------------------------
+    # route 1: fused whole-solve kernel
+    # ------------------------------------------------------------------------------------
+    def _solve_fused(self, problem, term_, field: BuiltinField, dt0) -> Optional[Solution]:
+        lib = _cabi.lib()
+        method, ctrl = self.step_method, self.step_size_controller
+        dev, D, Tt = problem.device, problem.data_dtype, problem.time_dtype
+        B, F, Tn = problem.batch_size, problem.n_features, problem.n_evaluation_points
+        cab_t = method.to_cabi()
+        cab_c = ctrl.to_cabi(method.convergence_order(), D, self.max_steps)
+        y0 = _launch.dense16(problem.y0)
+        t_start, t_end = problem.t_start.contiguous(), problem.t_end.contiguous()
+        prob = _cabi.Problem()
+        prob.B, prob.F, prob.T = B, F, Tn
+        prob.data_dtype, prob.time_dtype = _launch.dtype_id(D), _launch.dtype_id(Tt)
+        prob.y0, prob.t_start, prob.t_end = y0.data_ptr(), t_start.data_ptr(), t_end.data_ptr()
+        t_eval = None
+        if problem.t_eval is not None:
+            te = problem.t_eval
+            if te.stride(0) == 0 and (Tn <= 1 or te.stride(1) == 1):
+                t_eval, prob.t_eval_stride_b = te, 0
+            else:
+                t_eval, prob.t_eval_stride_b = te.contiguous(), Tn
+            prob.t_eval = t_eval.data_ptr()
+        dt0_c = None if dt0 is None else dt0.to(Tt).contiguous()
+        prob.dt0 = _launch.ptr(dt0_c)
+
+        ys = torch.empty((B, max(Tn, 1), F), dtype=D, device=dev)
+        n_steps = torch.empty(B, dtype=torch.long, device=dev)
+        n_accepted = torch.empty(B, dtype=torch.long, device=dev)
+        n_init = torch.empty(B, dtype=torch.long, device=dev)
+        status = torch.empty(B, dtype=torch.long, device=dev)
+        summary = torch.empty(4, dtype=torch.int32, device=dev)
+        sol = _cabi.SolutionOut()
+        sol.ys, sol.n_steps, sol.n_accepted = ys.data_ptr(), n_steps.data_ptr(), n_accepted.data_ptr()
+        sol.n_initialized, sol.status, sol.summary = n_init.data_ptr(), status.data_ptr(), summary.data_ptr()
+        fp = (C.c_double * _cabi.MAX_FIELD_PARAMS)(*field.params())
+        stream = _launch.stream_ptr(dev)
+
+        def run(cap: int):
+            _cabi.check(lib.tode_solve_fused(field.field_id, fp, C.byref(cab_t), C.byref(cab_c),
+                                             C.byref(prob), C.byref(sol), cap, stream), "tode_solve_fused")
+            return summary.tolist()  # the one host sync of the solve (n_f_evals lives on the CPU)
+
+        iters, first_fail, nonmono, _ = run(0)
+        if nonmono:
+            return None  # t_eval rows not monotone in time: the staged route has the general mode
+        if first_fail != _INT32_MAX and first_fail < iters:
+            # a failure stops the WHOLE batch at that iteration (adjoints.py:186-190): replay
+            # with every sample limited to the iterations the reference would have executed
+            iters, _, _, _ = run(first_fail)
+        stats: Dict[str, Any] = {}
+        term_.init(problem, stats)
+        if "n_f_evals" in stats:
+            n_stage_evals = cab_t.n_stages - 1  # FSAL
+            stats["n_f_evals"].fill_((2 if dt0 is None else 1) + n_stage_evals * iters)
+        stats["n_steps"], stats["n_accepted"], stats["n_initialized"] = n_steps, n_accepted, n_init
+        ts = problem.t_eval if problem.t_eval is not None else problem.t_end[:, None]
+        return Solution(ts=ts, ys=ys, stats=stats, status=status)
+
+    # ------------------------------------------------------------------------------------
+    # route 2: stage-wise kernels around an opaque f
+    # ------------------------------------------------------------------------------------
+    def _solve_staged(self, problem, term_, dt0, args, general: bool = False) -> Solution:
+        lib = _cabi.lib()
+        method, ctrl = self.step_method, self.step_size_controller
+        dev, D, Tt = problem.device, problem.data_dtype, problem.time_dtype
+        B, F, Tn = problem.batch_size, problem.n_features, problem.n_evaluation_points
+        cab_t = method.to_cabi()
+        cab_c = ctrl.to_cabi(method.convergence_order(), D, self.max_steps)
+        S = cab_t.n_stages
+        st = _launch.StagedState(problem, S, bool(cab_c.pid), general=general)
+        stream = _launch.stream_ptr(dev)
+        tab_p, ctrl_p, st_p = C.byref(cab_t), C.byref(cab_c), C.byref(st.c)
+        stats: Dict[str, Any] = {}
+        term_.init(problem, stats)
+
+        def vf(t, y):
+            out = term_.vf(t, y, stats, args)
+            if out.dtype != D:
+                raise TypeError(f"f returned {out.dtype}, expected the dtype of y0 ({D})")
+            if not out.is_contiguous() or out.data_ptr() % 16:
+                out = _launch.dense16(out)
+            return out
+
+        # ---- initial step size / state (adjoints.py:94-126) ---------------------------------
+        st.f0.copy_(vf(st.t_start, st.y))
+        n_init_evals = 1
+        if dt0 is None:
+            y1, t1 = st.y_stage[0], st.t_nodes[0]
+            _cabi.check(lib.tode_init_step_a(tab_p, ctrl_p, st_p, y1.data_ptr(), t1.data_ptr(), stream),
+                        "tode_init_step_a")
+            f1 = vf(t1, y1)
+            n_init_evals = 2
+            _cabi.check(lib.tode_init_step_b(tab_p, ctrl_p, st_p, f1.data_ptr(), stream), "tode_init_step_b")
+        else:
+            dt0_c = dt0.to(Tt).contiguous()
+            _cabi.check(lib.tode_init_with_dt0(tab_p, ctrl_p, st_p, dt0_c.data_ptr(), stream),
+                        "tode_init_with_dt0")
+        if general and Tn:
+            st.not_yet[:, 0] = (st.cursor == 0).to(torch.uint8)
+
+        # ---- the loop: never blocks on the iteration just launched ---------------------------
+        look = max(1, int(self.lookahead))
+        pinned = torch.zeros((look + 1, _cabi.CTL_WORDS), dtype=torch.int32).pin_memory()
+        events = [torch.cuda.Event() for _ in range(look + 1)]
+        kp = _cabi.KPtrs()
+        kp[0] = st.f0.data_ptr()
+        ks = [st.f0] + [None] * (S - 1)
+        stage, finish = lib.tode_erk_stage, lib.tode_erk_finish
+        y_stage, t_nodes = st.y_stage, st.t_nodes
+        launched = 0
+        ctl_host = None
+        while True:
+            for i in range(1, S):
+                y_i = y_stage[i - 1]
+                rc = stage(tab_p, i, st_p, kp, y_i.data_ptr(), stream)
+                if rc:
+                    _cabi.check(rc, "tode_erk_stage")
+                k_i = vf(t_nodes[i], y_i)
+                ks[i] = k_i  # keep alive until the finish kernel has consumed it
+                kp[i] = k_i.data_ptr()
+            rc = finish(tab_p, ctrl_p, st_p, kp, y_stage[S - 2].data_ptr(), stream)
+            if rc:
+                _cabi.check(rc, "tode_erk_finish")
+            slot = launched % (look + 1)
+            pinned[slot].copy_(st.ctl, non_blocking=True)
+            events[slot].record()
+            launched += 1
+            if launched >= look:
+                old = (launched - look) % (look + 1)
+                events[old].synchronize()
+                ctl_host = pinned[old].tolist()
+                if ctl_host[_cabi.CTL_NONMONO] and not general and Tn:
+                    # t_eval rows are not monotone in time: redo with the scan-all mask
+                    return self._solve_staged(problem, term_, dt0, args, general=True)
+                if ctl_host[_cabi.CTL_STOP]:
+                    break
+        torch.cuda.current_stream(dev).synchronize()
+        ctl_host = st.ctl.tolist()
+        iters = ctl_host[_cabi.CTL_ITERS]
+        if "n_f_evals" in stats:
+            # speculative iterations after the stop flag are no-ops on the device
+            stats["n_f_evals"].fill_(n_init_evals + (S - 1) * iters)
+        stats["n_steps"] = st.n_steps.to(torch.long)
+        stats["n_accepted"] = st.n_accepted.to(torch.long)
+        if Tn:
+            if general:
+                # adjoints.py:289-292
+                stats["n_initialized"] = torch.searchsorted(
+                    st.not_yet.int(), torch.ones((B, 1), dtype=torch.int, device=dev)).squeeze(dim=1)
+            else:
+                stats["n_initialized"] = st.cursor.to(torch.long)
+            ts = problem.t_eval
+        else:
+            stats["n_initialized"] = torch.ones(B, dtype=torch.long, device=dev)
+            ts = problem.t_end[:, None]
+        return Solution(ts=ts, ys=st.y_eval, stats=stats, status=st.status.to(torch.long))
+
+    # ------------------------------------------------------------------------------------
+    # route 3: foreign plug-ins (the reference's operator API)
+    # ------------------------------------------------------------------------------------
+    def _solve_generic(self, problem, term, term_, dt0, args) -> Solution:
+        method, controller = self.step_method, self.step_size_controller
+        dev, B = problem.device, problem.batch_size
+        t_end, t_eval = problem.t_end, problem.t_eval
+        sign = problem.time_direction.to(dtype=problem.time_dtype)
+        lo, hi = torch.minimum(problem.t_start, t_end), torch.maximum(problem.t_start, t_end)
+        stats: Dict[str, Any] = {}
+        term_.init(problem, stats)
+        t, y = problem.t_start, problem.y0
+        dt, ctrl_state, f0 = controller.init(term, problem, method.convergence_order(), dt0,
+                                              stats=stats, args=args)
+        meth_state = method.init(term, problem, f0, stats=stats, args=args)
+        dt = torch.clamp(dt, lo - t, hi - t)
+        if not self.backprop_through_step_size_control:
+            dt = dt.detach()
+        n_steps = torch.zeros(B, dtype=torch.long, device=dev)
+        n_accepted = torch.zeros(B, dtype=torch.long, device=dev)
+        running = torch.ones(B, dtype=torch.bool, device=dev)
+        pending = y_eval = None
+        if t_eval is not None:
+            y_eval = y.new_empty((B, problem.n_evaluation_points, problem.n_features))
+            pending = torch.ones_like(t_eval, dtype=torch.bool)
+            at_start = t_eval[:, 0] == t
+            y_eval[at_start, 0] = y[at_start]
+            pending[at_start, 0] = False
+        status = None
+        while True:
+            result, interp_data, meth_next, meth_status = method.step(
+                term, running, y, t, dt, meth_state, stats=stats, args=args)
+            accept, dt_next, ctrl_next, ctrl_status = controller.adapt_step_size(
+                t, dt, y, result, ctrl_state, stats)
+            if not self.backprop_through_step_size_control:
+                dt_next = dt_next.detach()
+            commit = accept & running
+            t = torch.where(commit, t + dt, t)
+            y = torch.where(commit[:, None], result.y, y)
+            meth_state = method.merge_states(commit, meth_next, meth_state)
+            n_steps += running
+            n_accepted += commit
+            running = torch.addcmul(-sign * t_end, sign, t) < 0.0
+
+            status = meth_status
+            if status is None:
+                status = ctrl_status
+            elif ctrl_status is not None:
+                status = torch.maximum(status, ctrl_status)
+            if self.max_steps is not None:
+                base = status if status is not None else status_codes.SUCCESS
+                status = torch.where(n_steps >= self.max_steps, status_codes.REACHED_MAX_STEPS, base)
+            go_on = running.any()
+            if status is not None:
+                go_on = go_on & (status == status_codes.SUCCESS).all()
+
+            if t_eval is not None:
+                crossed = (torch.addcmul(-sign[:, None] * t_eval, sign[:, None], t[:, None]) >= 0.0) & pending
+                if crossed.any():
+                    interp = method.build_interpolation(interp_data)
+                    rows, cols = crossed.nonzero(as_tuple=True)
+                    y_eval[rows, cols] = interp.evaluate(t_eval[rows, cols], rows)
+                    pending = pending & ~crossed
+
+            dt = torch.clamp(torch.where(running, dt_next, dt), lo - t, hi - t)
+            ctrl_state = controller.merge_states(running, ctrl_next, ctrl_state)
+            if bool(go_on):
+                continue
+            break
+
+        if status is None:
+            status = torch.zeros((), dtype=torch.long, device=dev).expand(B)
+        stats["n_steps"], stats["n_accepted"] = n_steps, n_accepted
+        if t_eval is not None:
+            stats["n_initialized"] = torch.searchsorted(
+                pending.int(), torch.ones((B, 1), dtype=torch.int, device=dev)).squeeze(dim=1)
+            return Solution(ts=t_eval, ys=y_eval, stats=stats, status=status)
+        interp = method.build_interpolation(interp_data)
+        y_end = interp.evaluate(t_end, torch.arange(B, device=dev))
+        stats["n_initialized"] = torch.ones(B, dtype=torch.long, device=dev)
+        return Solution(ts=t_end[:, None], ys=y_end[:, None], stats=stats, status=status)
+
+    def __repr__(self):
+        return (f"AutoDiffAdjoint(step_method={self.step_method}, "
+                f"step_size_controller={self.step_size_controller}, max_steps={self.max_steps}, "
+                f"backprop_through_step_size_control={self.backprop_through_step_size_control})")

@@ -1,0 +1,90 @@
+// C-ABI: tode_solve_fused -- whole solve of a built-in analytic field in one launch.
+#include <climits>
+
+#include "api_common.cuh"
+#include "erk_fused.cuh"
+
+namespace tode {
+
+__global__ void summary_init_kernel(int* summary) {
+  summary[0] = 0;
+  summary[1] = INT_MAX;
+  summary[2] = 0;
+  summary[3] = 0;
+}
+
+template <typename D, typename T, int F, int FIELD>
+static int launch_fused_f(const FusedArgs<D, T>& a, cudaStream_t stream) {
+  constexpr int kThreads = 128;
+  summary_init_kernel<<<1, 1, 0, stream>>>(a.summary);
+  const unsigned grid = (unsigned)((a.B + kThreads - 1) / kThreads);
+  solve_fused_kernel<D, T, F, FIELD><<<grid, kThreads, 0, stream>>>(a);
+  return launch_status();
+}
+
+template <typename D, typename T>
+static int launch_fused(int field, const double* fp, const tode_tableau* tab, const tode_controller* ctrl,
+                        const tode_problem* prob, const tode_solution* sol, int64_t iter_cap,
+                        cudaStream_t stream) {
+  if (tab->n_stages != kStagesFused) return TODE_ENOSUP;
+  const size_t row_bytes = sizeof(D) * prob->F;
+  const size_t al = row_bytes >= 16 ? 16 : row_bytes;
+  if (!aligned_to(prob->y0, al) || !aligned_to(sol->ys, al)) return TODE_EALIGN;
+  FusedArgs<D, T> a{};
+  a.tab = make_tab<D, T>(tab);
+  a.ctrl = make_ctrl<D, T>(ctrl);
+  for (int i = 0; i < TODE_MAX_FIELD_PARAMS; ++i) a.fp[i] = fp[i];
+  a.B = prob->B;
+  a.Tn = prob->T;
+  a.y0 = static_cast<const D*>(prob->y0);
+  a.t_start = static_cast<const T*>(prob->t_start);
+  a.t_end = static_cast<const T*>(prob->t_end);
+  a.t_eval = static_cast<const T*>(prob->t_eval);
+  a.te_stride = prob->t_eval_stride_b;
+  a.dt0 = static_cast<const T*>(prob->dt0);
+  a.ys = static_cast<D*>(sol->ys);
+  a.n_steps = reinterpret_cast<long long*>(sol->n_steps);
+  a.n_accepted = reinterpret_cast<long long*>(sol->n_accepted);
+  a.n_initialized = reinterpret_cast<long long*>(sol->n_initialized);
+  a.status = reinterpret_cast<long long*>(sol->status);
+  a.t_final = static_cast<T*>(sol->t_final);
+  a.dt_final = static_cast<T*>(sol->dt_final);
+  a.summary = sol->summary;
+  a.iter_cap = iter_cap;
+  a.e_init = round_exp<D>(1.0 / (double)tab->order);
+  if (a.B == 0) return 0;
+  switch (field) {
+    case TODE_FIELD_LINEAR:
+      switch (prob->F) {
+        case 1: return launch_fused_f<D, T, 1, TODE_FIELD_LINEAR>(a, stream);
+        case 2: return launch_fused_f<D, T, 2, TODE_FIELD_LINEAR>(a, stream);
+        case 3: return launch_fused_f<D, T, 3, TODE_FIELD_LINEAR>(a, stream);
+        case 4: return launch_fused_f<D, T, 4, TODE_FIELD_LINEAR>(a, stream);
+        default: return TODE_ENOSUP;
+      }
+    case TODE_FIELD_VAN_DER_POL:
+      if (prob->F != 2) return TODE_EINVAL;
+      return launch_fused_f<D, T, 2, TODE_FIELD_VAN_DER_POL>(a, stream);
+    case TODE_FIELD_LOTKA_VOLTERRA:
+      if (prob->F != 2) return TODE_EINVAL;
+      return launch_fused_f<D, T, 2, TODE_FIELD_LOTKA_VOLTERRA>(a, stream);
+    default:
+      return TODE_EINVAL;
+  }
+}
+
+}  // namespace tode
+
+using namespace tode;
+
+extern "C" int tode_solve_fused(int field, const double* field_params, const tode_tableau* tab,
+                                const tode_controller* ctrl, const tode_problem* prob,
+                                const tode_solution* sol, int64_t iter_cap, void* stream) {
+  if (!field_params || !tab || !ctrl || !prob || !sol) return TODE_EINVAL;
+  if (!prob->y0 || !prob->t_start || !prob->t_end || (prob->T > 0 && !prob->t_eval)) return TODE_EINVAL;
+  if (!sol->ys || !sol->n_steps || !sol->n_accepted || !sol->n_initialized || !sol->status || !sol->summary)
+    return TODE_EINVAL;
+#define CALL(D, T) launch_fused<D, T>(field, field_params, tab, ctrl, prob, sol, iter_cap, static_cast<cudaStream_t>(stream))
+  TODE_DISPATCH_DT(prob->data_dtype, prob->time_dtype, CALL);
+#undef CALL
+}
