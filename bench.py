@@ -1,0 +1,525 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native batch-parallel adaptive RK solve loop.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1] [--impl reference]
+
+One "step" = one complete solve of one batch of synthetic initial value problems through
+the public API (``AutoDiffAdjoint.solve``).  Metric (BASELINE.json): accepted RK steps/s in
+sample-steps (sum of ``stats["n_accepted"]`` / device time), whole job.
+
+Default workload = BASELINE.json ``configs[1]``: Van der Pol mu=10, Tsit5 + PIDController(1e-8,
+1e-8, 0.2, 0.5, 0), batch 2^20 per GPU, dim 2, fp64, t in [0, 20], no t_eval (SURVEY.md 8(d) C2;
+inputs from a CPU ``torch.Generator().manual_seed(1234)``).  For N > 1 (torchrun, one rank
+per GPU) every rank solves its own 2^20-sample slice of an N*2^20 batch (weak scaling, no
+collective in the step loop) and the step ends with the NCCL all-gather of ys / stats.
+
+The printed JSON line also carries
+  roofline          dominant kernel of the workload (algorithmic bytes / event time / measured peak)
+  roofline_kernels  the HBM-bound stage / finish kernels of the stage-wise path, timed live on
+                    2^24 x 2 fp32 operands (each operand 128 MiB > L2)
+  fp64_issue        achieved vs measured double-precision FMA rate (the fused C2 kernel is
+                    fp64-issue-bound, its HBM traffic is 80 B/sample)
+  cpu_baseline      the oracle port (oracle/, OpenMP on the host cores) on a bounded sample
+  e2e               same metric with HOST buffers: H2D of the inputs and D2H of ys + stats inside
+                    the timed region
+``--impl reference`` times the CPU path (the oracle port of the reference; the Python reference
+itself cannot travel to the GPU box) on the host cores and prints the same line shape.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torchode_b200 as to  # noqa: E402
+from torchode_b200 import _cabi, _launch  # noqa: E402
+from torchode_b200.fields import LinearDecay, LotkaVolterra, VanDerPol  # noqa: E402
+
+METRIC = "accepted_rk_steps_per_sec"
+UNIT = "sample-steps/s"
+
+
+# --------------------------------------------------------------------------------------------
+# workloads
+# --------------------------------------------------------------------------------------------
+class Workload:
+    def __init__(self, name, batch):
+        self.name, self.batch = name, batch
+
+    def describe(self):
+        raise NotImplementedError
+
+
+class C2(Workload):
+    """Van der Pol mu=10, Tsit5 + PID(1e-8,1e-8,.2,.5,0), fp64, t in [0,20], no t_eval."""
+
+    data_dtype, dtype_name = torch.float64, "f64"
+
+    def host_inputs(self, rank, batch):
+        g = torch.Generator().manual_seed(1234 + rank)
+        y0 = torch.rand(batch, 2, generator=g, dtype=torch.float64) * 4 - 2
+        return dict(y0=y0, t_start=torch.zeros(batch, dtype=torch.float64),
+                    t_end=torch.full((batch,), 20.0, dtype=torch.float64), t_eval=None)
+
+    def components(self):
+        field = VanDerPol(10.0)
+        term = to.ODETerm(field)
+        return field, to.Tsit5(term), to.PIDController(1e-8, 1e-8, 0.2, 0.5, 0.0, term=term)
+
+    def describe(self):
+        return ("configs[1]: Van der Pol mu=10, Tsit5+PID(1e-8,1e-8,0.2,0.5,0), fp64, t in [0,20], "
+                "no t_eval, fused whole-solve kernel")
+
+    def algorithmic_bytes(self, batch, T):
+        return batch * (16 + 16 + 16 + 32)  # y0, t_start+t_end, ys, 3 int64 stats + status
+
+
+class C3(Workload):
+    """Lotka-Volterra, Dopri5 + I(1e-6,1e-3), fp32, 100 shared t_eval points in [0,10]."""
+
+    data_dtype, dtype_name = torch.float32, "f32"
+
+    def host_inputs(self, rank, batch):
+        g = torch.Generator().manual_seed(1234 + rank)
+        y0 = 1 + torch.rand(batch, 2, generator=g)
+        t_row = torch.linspace(0, 10, 100)
+        return dict(y0=y0, t_start=torch.zeros(batch), t_end=torch.full((batch,), 10.0), t_eval=t_row)
+
+    def components(self):
+        field = LotkaVolterra()
+        term = to.ODETerm(field)
+        return field, to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term)
+
+    def describe(self):
+        return ("configs[2]: Lotka-Volterra, Dopri5+I(1e-6,1e-3), fp32, 100 t_eval points in [0,10] "
+                "(broadcast row), fused whole-solve kernel")
+
+    def algorithmic_bytes(self, batch, T):
+        return batch * (8 + 8 + T * 8 + 32)
+
+
+class C1(Workload):
+    """README example."""
+
+    data_dtype, dtype_name = torch.float32, "f32"
+
+    def host_inputs(self, rank, batch):
+        return dict(y0=torch.tensor([[1.2], [5.0]]), t_start=torch.tensor([0.0, 3.0]),
+                    t_end=torch.tensor([5.0, 4.0]),
+                    t_eval=torch.stack((torch.linspace(0, 5, 10), torch.linspace(3, 4, 10))))
+
+    def components(self):
+        field = LinearDecay(-0.5)
+        term = to.ODETerm(field)
+        return field, to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term)
+
+    def describe(self):
+        return "configs[0]: README example, Dopri5+I(1e-6,1e-3), f=-0.5y, batch 2, 10 t_eval"
+
+    def algorithmic_bytes(self, batch, T):
+        return batch * (4 + 8 + T * 8 + 32)
+
+
+WORKLOADS = {"c2": (C2, 1 << 20), "c3": (C3, 1 << 24), "c1": (C1, 2)}
+
+
+def make_problem(host, device):
+    dev = {k: (None if v is None else v.to(device)) for k, v in host.items()}
+    t_eval = dev["t_eval"]
+    if t_eval is not None and t_eval.ndim == 1:
+        t_eval = t_eval.expand(dev["y0"].shape[0], -1)  # stride-0 row: never materialised
+    return to.InitialValueProblem(dev["y0"], dev["t_start"], dev["t_end"], t_eval)
+
+
+# --------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        busy = [s for s in sm if s >= 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def flush_l2(buf):
+    buf.add_(1)  # 512 MiB read+write > 126 MB L2
+
+
+def ev_pair():
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port on the host cores, bounded sample
+# --------------------------------------------------------------------------------------------
+def cpu_run(workload, sample_batch, repeats=1):
+    from oracle import oracle as orc
+    from torchode_b200.single_step_methods import ExplicitRungeKutta  # noqa: F401
+
+    field, method, ctrl = workload.components()
+    host = workload.host_inputs(0, sample_batch)
+    tab = method.to_cabi()
+    cc = ctrl.to_cabi(method.convergence_order(), host["y0"].dtype)
+    t_eval = host["t_eval"]
+    if t_eval is not None and t_eval.ndim == 1:
+        t_eval = np.broadcast_to(t_eval.numpy(), (sample_batch, t_eval.shape[0]))
+    elif t_eval is not None:
+        t_eval = t_eval.numpy()
+    args = (field.field_id, field.params(), tab, cc, host["y0"].numpy(), host["t_start"].numpy(),
+            host["t_end"].numpy(), t_eval)
+    orc.lib()
+    best, out = None, None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        out = orc.solve_builtin(*args)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    acc = int(out["n_accepted"].sum())
+    return acc / best, best, acc
+
+
+def cpu_sample_size(workload):
+    return {"c2": 1 << 17, "c3": 1 << 20, "c1": 2}[workload.name]
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args, workload):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sb = cpu_sample_size(workload)
+    values, times = [], []
+    for i in range(args.warmup + args.steps):
+        v, t, _ = cpu_run(workload, sb)
+        if i >= args.warmup:
+            values.append(v)
+            times.append(t)
+    value = sum(values) / len(values)
+    sample = (f"{sb} of {workload.batch} samples of the same seeded workload per step, oracle port "
+              f"(plain C + OpenMP, lock-step like the reference)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": workload.dtype_name,
+        "data": "synthetic", "config": {"workload": workload.describe(), "batch_per_step": sb},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_cores(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+# live roofline of the stage-wise (path A) kernels
+# --------------------------------------------------------------------------------------------
+def measure_path_a_kernels(device, hbm_peak, reps=5):
+    lib = _cabi.lib()
+    B, F = 1 << 24, 2
+    g = torch.Generator().manual_seed(7)
+    y0 = (1 + torch.rand(B, F, generator=g)).to(device)
+    problem = to.InitialValueProblem(y0, torch.zeros(B, device=device), torch.full((B,), 1e6, device=device))
+    method = to.Dopri5()
+    ctrl = to.IntegralController(1e-6, 1e-3)
+    cab_t, cab_c = method.to_cabi(), ctrl.to_cabi(5, torch.float32)
+    st = _launch.StagedState(problem, 7, False)
+    ks = [st.f0] + [torch.empty_like(y0) for _ in range(6)]
+    for k in ks:
+        k.copy_(torch.randn(B, F, generator=g).to(device) * 0.5)
+    dt0 = torch.full((B,), 1e-3, device=device)
+    stream = _launch.stream_ptr(device)
+    _cabi.check(lib.tode_init_with_dt0(C.byref(cab_t), C.byref(cab_c), C.byref(st.c), dt0.data_ptr(), stream),
+                "init")
+    kp = _launch.kptrs(ks)
+    e, et = 4, 4
+    out = []
+    for i in range(1, 7):
+        times = []
+        for _ in range(reps + 1):
+            e0, e1 = ev_pair()
+            e0.record()
+            _cabi.check(lib.tode_erk_stage(C.byref(cab_t), i, C.byref(st.c), kp, st.y_stage[i - 1].data_ptr(),
+                                           stream), "stage")
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = statistics.median(times[1:])
+        byts = (i + 2) * B * F * e + B * (et + 1)
+        out.append({"kernel": f"erk_stage_kernel<f32,f32,VEC=2,NK={i}>", "bytes": byts, "ms": ms,
+                    "achieved": byts / ms / 1e6, "frac": byts / ms / 1e6 / hbm_peak})
+    # finish: reset the mutable per-sample state before every launch
+    times, n_acc = [], 0
+    saved = dict(t=st.t.clone(), dt=st.dt.clone(), y=st.y.clone(), f0=st.f0.clone())
+    for _ in range(reps + 1):
+        st.t.copy_(saved["t"]); st.dt.copy_(saved["dt"]); st.y.copy_(saved["y"]); st.f0.copy_(saved["f0"])
+        st.running.fill_(1); st.n_steps.zero_(); st.n_accepted.zero_(); st.ctl.zero_()
+        e0, e1 = ev_pair()
+        e0.record()
+        _cabi.check(lib.tode_erk_finish(C.byref(cab_t), C.byref(cab_c), C.byref(st.c), kp,
+                                        st.y_stage[5].data_ptr(), stream), "finish")
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+        n_acc = int(st.n_accepted.sum())
+    ms = statistics.median(times[1:])
+    # reads: y, y1, k0..k6 (9 rows) + t, dt, t_start, t_end, n_steps, running; writes: t, dt, n_steps,
+    # status, running, 6 t_nodes; accepted rows additionally write y and f0 (+ n_accepted r/w)
+    byts = 9 * B * F * e + B * (4 * et + 4 + 1) + B * (2 * et + 4 + 4 + 1 + 6 * et) + n_acc * (2 * F * e + 8)
+    out.append({"kernel": "erk_finish_kernel<f32,f32,G=1,VEC=2>", "bytes": byts, "ms": ms,
+                "achieved": byts / ms / 1e6, "frac": byts / ms / 1e6 / hbm_peak,
+                "accepted_fraction": n_acc / B})
+    return out
+
+
+def measure_fp64_peak(device):
+    lib = _cabi.lib()
+    n = int(lib.tode_bench_fp64_fma_threads())
+    sink = torch.empty(n, dtype=torch.float64, device=device)
+    n_fma = C.c_int64(0)
+    best = None
+    for _ in range(4):
+        e0, e1 = ev_pair()
+        e0.record()
+        _cabi.check(lib.tode_bench_fp64_fma(4096, sink.data_ptr(), C.byref(n_fma), _launch.stream_ptr(device)),
+                    "fp64 peak")
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return n_fma.value / best / 1e9  # GFMA/s -> TFMA/s * 1e3
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the config's)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / kernel rooflines")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    cls, batch = WORKLOADS[args.workload]
+    workload = cls(args.workload, args.batch or batch)
+    if args.impl == "reference":
+        return run_reference_arm(args, workload)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference "
+                         "for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    from torchode_b200.distributed import gather_solution
+
+    hbm_peak, peak_src = peaks()
+    B = workload.batch
+    host = workload.host_inputs(rank, B)
+    host_pinned = {k: (None if v is None else v.pin_memory()) for k, v in host.items()}
+    problem = make_problem(host, device)
+    T = problem.n_evaluation_points
+    field, method, ctrl = workload.components()
+    solver = to.AutoDiffAdjoint(method, ctrl)
+    l2buf = torch.zeros(128 << 20, dtype=torch.float32, device=device)  # 512 MiB
+
+    def step():
+        sol = solver.solve(problem)
+        if world > 1:
+            sol = gather_solution(sol, B * world, ts=None if T == 0 else problem.t_eval)
+        return sol
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            sol = step()
+        sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+        barrier()
+        times = []
+        t_wall = time.perf_counter()
+        for _ in range(args.steps):
+            flush_l2(l2buf)
+            e0, e1 = ev_pair()
+            e0.record()
+            sol = step()
+            e1.record()
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1))
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+        clocks = sampler.stop() if sampler is not None else None
+
+        # per-rank accepted steps of ONE step (every step solves the same inputs)
+        local = solver.solve(problem)
+        acc_local = int(local.stats["n_accepted"].sum())
+        iters = (int(local.stats["n_f_evals"][0]) - 2) // 6
+        n_status = int((local.status != 0).sum())
+        mean_steps = float(local.stats["n_steps"].float().mean())
+
+        total_ms = torch.tensor([sum(times)], dtype=torch.float64, device=device)
+        acc = torch.tensor([acc_local], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        ms_per_step = float(total_ms) / args.steps
+        value = float(acc) / (ms_per_step * 1e-3)
+
+        # ---- end-to-end through the public API with host buffers (every rank, max over ranks)
+        h2d = sum(v.numel() * v.element_size() for v in host_pinned.values() if v is not None)
+        e2e_times, d2h = [], 0
+        for i in range(2 + max(3, args.steps // 2)):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            prob_e = make_problem(host_pinned, device)
+            s = solver.solve(prob_e)
+            outs = [s.ys, s.stats["n_steps"], s.stats["n_accepted"], s.stats["n_initialized"], s.status]
+            host_out = [o.to("cpu", non_blocking=True) for o in outs]
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            d2h = sum(o.numel() * o.element_size() for o in host_out)
+            if i >= 2:
+                e2e_times.append(dt)
+        e2e_s = torch.tensor([statistics.median(e2e_times)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e_value = float(acc) / float(e2e_s)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (the fused whole-solve kernel) -----------------------
+    kernel_ms = statistics.median(times) if world == 1 else ms_per_step
+    alg_bytes = workload.algorithmic_bytes(B, T)
+    roofline = {
+        "kernel": "solve_fused_kernel", "bound": "hbm", "achieved": alg_bytes / kernel_ms / 1e6,
+        "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / kernel_ms / 1e6 / hbm_peak, "traffic": None,
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+        "note": ("whole solve in registers: HBM is touched only for inputs/outputs; for C2 the kernel is "
+                 "fp64-issue-bound, see fp64_issue; the HBM-bound kernels of the stage-wise path are in "
+                 "roofline_kernels"),
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": workload.dtype_name, "data": "synthetic",
+        "config": {"workload": workload.describe(), "batch_per_gpu": B, "global_batch": B * world,
+                   "features": int(problem.n_features), "t_eval_points": T,
+                   "l2": "512 MiB buffer rewritten between timed steps (L2 flush)",
+                   "loop_iterations": iters, "mean_n_steps": mean_steps,
+                   "samples_with_failure_status": n_status,
+                   "multi_gpu": "independent batch slices, NCCL all-gather of ys/stats after the solve"},
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": float(e2e_s) * 1e3},
+        "gpu_launches": 2 * args.steps,  # summary_init_kernel + solve_fused_kernel per step
+        "wall_s_timed_region": t_wall,
+    }
+    if clocks is not None:
+        line["clocks"] = clocks
+    if not args.no_extras and world == 1:
+        try:
+            peak_fma = measure_fp64_peak(device)  # GFMA/s
+            line["fp64_issue"] = {"peak_gfma_per_s": peak_fma, "peak_source": "tode_bench_fp64_fma, measured live"}
+        except Exception as exc:  # measurement aid only
+            line["fp64_issue"] = {"error": str(exc)}
+        try:
+            line["roofline_kernels"] = measure_path_a_kernels(device, hbm_peak)
+        except Exception as exc:
+            line["roofline_kernels"] = {"error": str(exc)}
+        try:
+            sb = cpu_sample_size(workload)
+            v, t, _ = cpu_run(workload, sb)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": cpu_cores(), "kind": "port",
+                "sample": f"{sb} of {B} samples of the same seeded workload, oracle port (plain C + OpenMP), "
+                          f"{t:.1f} s"}
+        except Exception as exc:
+            line["cpu_baseline"] = {"error": str(exc)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -258,6 +258,13 @@ int tode_interp_eval(const tode_tableau* tab, int32_t data_dtype, int32_t time_d
                      const void* y0, const void* y1, const void* const* k, const void* t,
                      const int64_t* idx, void* out, void* stream);
 
+/* Measurement aid for bench.py (not on the solve path): every thread of a machine-filling
+ * grid runs `iters` rounds of 8 independent double-precision FMA chains; writes one double
+ * per thread to `sink` (at least tode_bench_fp64_fma_threads() doubles).  Returns the number
+ * of FMAs executed through *n_fma_out (host pointer). */
+int64_t tode_bench_fp64_fma_threads(void);
+int tode_bench_fp64_fma(int64_t iters, void* sink, int64_t* n_fma_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

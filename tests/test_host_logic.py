@@ -1,0 +1,239 @@
+"""Host-side logic on CPU: the generic plug-in route of AutoDiffAdjoint.solve (the reference's
+operator API: arbitrary SingleStepMethod / StepSizeController objects), parameter packing,
+input validation, and the loud refusal to run built-in components without CUDA.
+
+The scenarios mirror what the reference's own loop tests pin (tests/adjoint_test.py:26-319):
+exact n_steps / n_accepted / n_initialized lists, rejected steps retrying from the same t,
+several evaluation points inside one step, max_steps, status codes stopping the batch."""
+import math
+
+import pytest
+import torch
+
+import torchode_b200 as to
+from torchode_b200 import _cabi
+from torchode_b200.single_step_methods import SingleStepMethod, StepResult
+from torchode_b200.step_size_controllers import StepSizeController, max_norm, rms_norm
+
+
+def exact(t):
+    """closed-form solution used by the scripted step method: y(t) = sin(t) + t^2"""
+    return (torch.sin(t) + t * t)[..., None]
+
+
+class ExactInterp:
+    def evaluate(self, t, idx):
+        return exact(t)
+
+
+class ExactStep(SingleStepMethod):
+    """'Steps' by evaluating the closed form at t + dt; error and status are scripted."""
+
+    def __init__(self, status=0, error=None):
+        super().__init__()
+        self.term = to.ODETerm(lambda t, y: (_ for _ in ()).throw(AssertionError("f must not be called")))
+        self.status, self.error = status, error
+        self.calls = []
+
+    def init(self, term, problem, f0, *, stats, args):
+        return None
+
+    def step(self, term, running, y, t, dt, state, *, stats, args):
+        self.calls.append((t.clone(), dt.clone(), running.clone()))
+        y1 = exact(t + dt)
+        err = torch.zeros_like(y1) if self.error is None else self.error(t)
+        status = self.status(t + dt) if callable(self.status) else torch.full_like(t, self.status, dtype=torch.long)
+        return StepResult(y1, err), None, state, status
+
+    def merge_states(self, accept, current, previous):
+        return current
+
+    def build_interpolation(self, data):
+        return ExactInterp()
+
+    def convergence_order(self):
+        return 3
+
+
+class Scripted(StepSizeController):
+    """dt0, then per-iteration scripted (dt_next, accept, status): constants or lists consumed in order."""
+
+    def __init__(self, dt0, dt, accept=True, status=0):
+        super().__init__()
+        self.dt0, self.script = dt0, dict(dt=dt, accept=accept, status=status)
+        self.i = 0
+
+    def _get(self, key, shape, dtype):
+        v = self.script[key]
+        if isinstance(v, list) and len(v) and isinstance(v[0], (list, tuple)):
+            v = v[min(self.i, len(v) - 1)]
+        return torch.as_tensor(v, dtype=dtype).expand(shape)
+
+    def init(self, term, problem, order, dt0, *, stats, args):
+        shape = (problem.batch_size,)
+        return torch.as_tensor(self.dt0, dtype=problem.time_dtype).expand(shape), {}, None
+
+    def adapt_step_size(self, t0, dt, y0, step_result, state, stats):
+        out = (self._get("accept", dt.shape, torch.bool), self._get("dt", dt.shape, dt.dtype), state,
+               self._get("status", dt.shape, torch.long))
+        self.i += 1
+        return out
+
+    def merge_states(self, running, current, previous):
+        return current
+
+
+def problem_of(t_eval=None, t_start=None, t_end=None):
+    if t_eval is not None:
+        t_eval = torch.tensor(t_eval)
+        t_start = t_eval[:, 0] if t_start is None else torch.tensor(t_start)
+        t_end = t_eval[:, -1] if t_end is None else torch.tensor(t_end)
+    else:
+        t_start, t_end = torch.tensor(t_start), torch.tensor(t_end)
+    return to.InitialValueProblem(exact(t_start), t_start, t_end, t_eval)
+
+
+def test_evaluates_at_every_evaluation_point():
+    problem = problem_of([[0.0, 2.0], [2.0, 4.0], [0.5, 2.5]])
+    sol = to.AutoDiffAdjoint(ExactStep(), Scripted(0.3, 0.3)).solve(problem)
+    assert sol.status.tolist() == [0, 0, 0]
+    assert sol.stats["n_steps"].tolist() == [7, 7, 7]
+    assert sol.stats["n_accepted"].tolist() == [7, 7, 7]
+    assert sol.stats["n_initialized"].tolist() == [2, 2, 2]
+    assert sol.ts is problem.t_eval
+    assert torch.equal(sol.ys, exact(problem.t_eval))
+
+
+def test_samples_step_independently():
+    problem = problem_of([[0.0, 0.15, 1.0], [1.0, 1.9, 2.0]])
+    sol = to.AutoDiffAdjoint(ExactStep(), Scripted([0.1, 0.3], [0.5, 0.125])).solve(problem)
+    assert sol.stats["n_steps"].tolist() == [3, 7]
+    assert sol.stats["n_accepted"].tolist() == [3, 7]
+    assert sol.stats["n_initialized"].tolist() == [3, 3]
+    assert torch.equal(sol.ys, exact(problem.t_eval))
+
+
+def test_several_evaluation_points_inside_one_step():
+    problem = problem_of([[0.0, 0.25, 0.33, 1.0]])
+    sol = to.AutoDiffAdjoint(ExactStep(), Scripted(0.1, 0.5)).solve(problem)
+    assert sol.stats["n_steps"].tolist() == [3]
+    assert sol.stats["n_initialized"].tolist() == [4]
+    assert torch.equal(sol.ys, exact(problem.t_eval))
+
+
+def test_no_t_eval_reports_t_end():
+    problem = problem_of(t_start=[0.0, 5.0, 2.0], t_end=[10.0, 9.0, 4.5])
+    sol = to.AutoDiffAdjoint(ExactStep(), Scripted([0.5001, 0.2501, 1.0], [0.5001, 0.2501, 1.0])).solve(problem)
+    assert sol.stats["n_steps"].tolist() == [20, 16, 3]
+    assert sol.stats["n_initialized"].tolist() == [1, 1, 1]
+    assert sol.ts[:, 0].tolist() == [10.0, 9.0, 4.5]
+    assert sol.ys.shape == (3, 1, 1)
+    assert torch.allclose(sol.ys[:, 0], exact(problem.t_end))
+
+
+def test_rejected_steps_retry_from_the_same_time():
+    problem = problem_of([[0.0, 1.0], [1.0, 2.0]])
+    method = ExactStep()
+    accept = [[True, True], [False, True], [True, False], [True, True]]
+    sol = to.AutoDiffAdjoint(method, Scripted(0.4, 0.4, accept=accept)).solve(problem)
+    t_seen = torch.stack([c[0] for c in method.calls])
+    assert torch.allclose(t_seen[:4], torch.tensor([[0.0, 1.0], [0.4, 1.4], [0.4, 1.8], [0.8, 1.8]]))
+    assert sol.stats["n_steps"].tolist() == [4, 4]
+    assert sol.stats["n_accepted"].tolist() == [3, 3]
+    assert torch.equal(sol.ys, exact(problem.t_eval))
+
+
+def test_f_is_never_evaluated_outside_the_time_domain():
+    problem = problem_of([[0.0, 1.0], [3.0, 2.0]])  # second sample runs backwards
+    method = ExactStep()
+    to.AutoDiffAdjoint(method, Scripted([0.7, -0.7], [0.7, -0.7])).solve(problem)
+    for t, dt, _ in method.calls:
+        t1 = t + dt
+        assert (t1[0] <= 1.0 + 1e-6) and (t1[1] >= 2.0 - 1e-6)
+
+
+def test_max_steps_sets_status_for_unfinished_samples_only():
+    t_eval = torch.tensor([[1.0, 4.9], [2.0, 13.0]])
+    problem = to.InitialValueProblem(torch.zeros(2, 1), t_eval[:, 0], t_eval[:, -1], t_eval)
+    solver = to.AutoDiffAdjoint(ExactStep(), to.FixedStepController(), max_steps=7)
+    sol = solver.solve(problem, dt0=torch.ones(2))
+    assert sol.status.tolist() == [0, to.Status.REACHED_MAX_STEPS.value]
+    assert sol.stats["n_steps"].tolist() == [4, 7]
+    assert sol.stats["n_initialized"].tolist() == [2, 1]
+
+
+@pytest.mark.parametrize("who", ["method", "controller"])
+def test_non_success_status_stops_the_whole_batch(who):
+    problem = problem_of([[0.0, 1.0], [0.0, 1.0]])
+    bad = [[0, 0], [0, to.Status.GENERAL_ERROR.value]]
+    if who == "method":
+        n = {"i": 0}
+
+        def status(t):
+            s = torch.tensor(bad[min(n["i"], 1)])
+            n["i"] += 1
+            return s
+        solver = to.AutoDiffAdjoint(ExactStep(status=status), Scripted(0.1, 0.1))
+    else:
+        solver = to.AutoDiffAdjoint(ExactStep(), Scripted(0.1, 0.1, status=bad))
+    sol = solver.solve(problem)
+    assert sol.status.tolist() == [0, 1]
+    assert sol.stats["n_steps"].tolist() == [2, 2]
+    assert sol.stats["n_initialized"].tolist() == [1, 1]
+
+
+def test_finished_samples_keep_their_step_size_clamped_to_zero():
+    problem = problem_of([[0.0, 0.2], [0.0, 1.0]])
+    method = ExactStep()
+    to.AutoDiffAdjoint(method, Scripted(0.2, 0.2)).solve(problem)
+    dts = torch.stack([c[1] for c in method.calls])
+    assert dts[0].tolist() == pytest.approx([0.2, 0.2])
+    assert (dts[1:, 0] == 0).all()  # the finished sample is stepped with dt == 0 (masked)
+
+
+def test_builtin_components_refuse_cpu_tensors_loudly():
+    term = to.ODETerm(lambda t, y: -y)
+    solver = to.AutoDiffAdjoint(to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        solver.solve(to.InitialValueProblem(torch.ones(2, 1), torch.zeros(2), torch.ones(2)))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        to.solve_ivp(lambda t, y: -y, torch.ones(2, 1), torch.linspace(0, 1, 3))
+
+
+def test_problem_validation_and_properties():
+    with pytest.raises(AssertionError):
+        to.InitialValueProblem(torch.ones(3), torch.zeros(3), torch.ones(3))  # y0 must be 2-d
+    with pytest.raises(AssertionError):
+        to.InitialValueProblem(torch.ones(3, 1), torch.zeros(3), torch.ones(3, dtype=torch.float64))
+    p = to.InitialValueProblem(torch.ones(3, 2), t_eval=torch.tensor([[0.0, 1.0], [1.0, 0.0], [2.0, 2.0]]))
+    assert p.time_direction.tolist() == [1, -1, -1]  # equal times count as backwards
+    assert (p.batch_size, p.n_features, p.n_evaluation_points) == (3, 2, 2)
+    assert p.data_dtype == torch.float32 and p.time_dtype == torch.float32
+
+
+def test_controller_packing_matches_the_reference_conventions():
+    c = to.PIDController(1e-6, 1e-3, 0.2, 0.5, 0.1, dt_min=1e-4, norm=max_norm).to_cabi(5, torch.float64, 11)
+    assert c.pid == 1 and c.norm == _cabi.NORM_MAX and c.has_dt_min == 1 and c.has_dt_max == 0
+    assert c.atol == float(torch.tensor(1e-6)) and c.rtol == float(torch.tensor(1e-3))  # fp32-rounded
+    assert c.exp_ratio == -(0.5 / 5 + 0.2 / 5 + 0.1 / 5) and c.exp_prev == 0.2 / 5 + 2 * (0.1 / 5)
+    assert c.exp_prev2 == -(0.1 / 5) and c.max_steps == 11 and c.almost_zero == 1e-38
+    i = to.IntegralController(1e-6, 1e-3).to_cabi(5, torch.float32)
+    assert i.pid == 0 and i.norm == _cabi.NORM_RMS and i.exp_ratio == -(1.0 / 5) and i.max_steps == -1
+    assert not to.IntegralController(1e-6, 1e-3, norm=lambda y: y.abs().sum(1)).fusable()
+
+
+def test_term_counts_evaluations_and_passes_args():
+    seen = []
+    term = to.ODETerm(lambda t, y, a: seen.append(a) or y, with_args=True)
+    stats = {}
+    p = to.InitialValueProblem(torch.ones(4, 1), torch.zeros(4), torch.ones(4))
+    term.init(p, stats)
+    marker = object()
+    term.vf(p.t_start, p.y0, stats, marker)
+    term.vf(p.t_start, p.y0, stats, marker)
+    assert stats["n_f_evals"].tolist() == [2, 2, 2, 2] and stats["n_f_evals"].device.type == "cpu"
+    assert seen == [marker, marker]
+    quiet = to.ODETerm(lambda t, y: y, with_stats=False)
+    stats = {}
+    quiet.init(p, stats)
+    assert "n_f_evals" not in stats

@@ -147,6 +147,8 @@ PROTOTYPES = {
          _vp],
     ),
     "tode_time_nodes": (C.c_int, [_P(Tableau), C.c_int32, C.c_int64, _vp, _vp, _vp, _vp]),
+    "tode_bench_fp64_fma_threads": (C.c_int64, []),
+    "tode_bench_fp64_fma": (C.c_int, [C.c_int64, _vp, _P(C.c_int64), _vp]),
     "tode_adapt_step_size": (
         C.c_int,
         [_P(Controller), C.c_int32, C.c_int32, C.c_int64, C.c_int64] + [_vp] * 12 + [_vp],
