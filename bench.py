@@ -276,25 +276,31 @@ def run_reference_arm(args, workload):
 # --------------------------------------------------------------------------------------------
 # live roofline of the stage-wise (path A) kernels
 # --------------------------------------------------------------------------------------------
-def measure_path_a_kernels(device, hbm_peak, reps=5):
+def measure_path_a_kernels(device, hbm_peak, reps=5, B=1 << 24, F=2, dtype=torch.float32):
+    """Times tode_erk_stage (i = 1..6) and tode_erk_finish alone, CUDA events on the launch stream,
+    on operands far larger than L2, every sample running.  Algorithmic bytes per launch:
+    stage i: (i + 2) rows of F elements + dt + running flag per sample; finish: 9 rows read, the
+    per-sample scalars read/written, 2 rows written for every accepted sample."""
     lib = _cabi.lib()
-    B, F = 1 << 24, 2
     g = torch.Generator().manual_seed(7)
-    y0 = (1 + torch.rand(B, F, generator=g)).to(device)
-    problem = to.InitialValueProblem(y0, torch.zeros(B, device=device), torch.full((B,), 1e6, device=device))
+    y0 = (1 + torch.rand(B, F, generator=g, dtype=dtype)).to(device)
+    zeros = torch.zeros(B, device=device, dtype=dtype)
+    problem = to.InitialValueProblem(y0, zeros, torch.full((B,), 1e6, device=device, dtype=dtype))
     method = to.Dopri5()
     ctrl = to.IntegralController(1e-6, 1e-3)
-    cab_t, cab_c = method.to_cabi(), ctrl.to_cabi(5, torch.float32)
+    cab_t, cab_c = method.to_cabi(), ctrl.to_cabi(5, dtype)
     st = _launch.StagedState(problem, 7, False)
     ks = [st.f0] + [torch.empty_like(y0) for _ in range(6)]
-    for k in ks:
-        k.copy_(torch.randn(B, F, generator=g).to(device) * 0.5)
-    dt0 = torch.full((B,), 1e-3, device=device)
+    base = torch.randn(B, F, generator=g, dtype=dtype).to(device) * 0.5
+    for j, k in enumerate(ks):
+        k.copy_(base + 1e-3 * j)  # smooth "derivatives": small error estimate, steps get accepted
+    dt0 = torch.full((B,), 1e-3, device=device, dtype=dtype)
     stream = _launch.stream_ptr(device)
     _cabi.check(lib.tode_init_with_dt0(C.byref(cab_t), C.byref(cab_c), C.byref(st.c), dt0.data_ptr(), stream),
                 "init")
     kp = _launch.kptrs(ks)
-    e, et = 4, 4
+    e = et = y0.element_size()
+    tag = f"{'f32' if e == 4 else 'f64'},B={B},F={F}"
     out = []
     for i in range(1, 7):
         times = []
@@ -308,7 +314,7 @@ def measure_path_a_kernels(device, hbm_peak, reps=5):
             times.append(e0.elapsed_time(e1))
         ms = statistics.median(times[1:])
         byts = (i + 2) * B * F * e + B * (et + 1)
-        out.append({"kernel": f"erk_stage_kernel<f32,f32,VEC=2,NK={i}>", "bytes": byts, "ms": ms,
+        out.append({"kernel": f"erk_stage_kernel<{tag},NK={i}>", "bytes": byts, "ms": ms,
                     "achieved": byts / ms / 1e6, "frac": byts / ms / 1e6 / hbm_peak})
     # finish: reset the mutable per-sample state before every launch
     times, n_acc = [], 0
@@ -328,7 +334,7 @@ def measure_path_a_kernels(device, hbm_peak, reps=5):
     # reads: y, y1, k0..k6 (9 rows) + t, dt, t_start, t_end, n_steps, running; writes: t, dt, n_steps,
     # status, running, 6 t_nodes; accepted rows additionally write y and f0 (+ n_accepted r/w)
     byts = 9 * B * F * e + B * (4 * et + 4 + 1) + B * (2 * et + 4 + 4 + 1 + 6 * et) + n_acc * (2 * F * e + 8)
-    out.append({"kernel": "erk_finish_kernel<f32,f32,G=1,VEC=2>", "bytes": byts, "ms": ms,
+    out.append({"kernel": f"erk_finish_kernel<{tag}>", "bytes": byts, "ms": ms,
                 "achieved": byts / ms / 1e6, "frac": byts / ms / 1e6 / hbm_peak,
                 "accepted_fraction": n_acc / B})
     return out
@@ -349,7 +355,7 @@ def measure_fp64_peak(device):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         best = ms if best is None else min(best, ms)
-    return n_fma.value / best / 1e9  # GFMA/s -> TFMA/s * 1e3
+    return n_fma.value / best / 1e9  # FMA per ms / 1e9 = tera-FMA per second
 
 
 # --------------------------------------------------------------------------------------------
@@ -497,8 +503,8 @@ def main():
         line["clocks"] = clocks
     if not args.no_extras and world == 1:
         try:
-            peak_fma = measure_fp64_peak(device)  # GFMA/s
-            line["fp64_issue"] = {"peak_gfma_per_s": peak_fma, "peak_source": "tode_bench_fp64_fma, measured live"}
+            peak_fma = measure_fp64_peak(device)  # tera-FMA/s
+            line["fp64_issue"] = {"peak_tfma_per_s": peak_fma, "peak_source": "tode_bench_fp64_fma, measured live"}
         except Exception as exc:  # measurement aid only
             line["fp64_issue"] = {"error": str(exc)}
         try:

@@ -36,9 +36,10 @@ static inline Tt FN(dir_of)(Tt t_start, Tt t_end) { return t_end > t_start ? (Tt
  * max: NaN-propagating max |x_i|.  rms: sqrt(sum_i (x_i / sqrt(F))^2) with the squares
  * summed in the CANONICAL ORDER that the kernels' lane geometry defines:
  *   VEC = widest <=16-byte vector (in elements) dividing F, N = F / VEC vectors,
- *   G = min(32, next_pow2(N)) lanes; lane l accumulates vectors l, l+G, ... in ascending
- *   order (first square a plain product, later ones FMAs); the G partials are combined by
- *   an xor-butterfly with strides 1, 2, ..., G/2.
+ *   G = min(32, next_pow2(N)) lanes; the row is cut into chunks of 1024 vectors; inside a
+ *   chunk lane l accumulates vectors l, l+G, ... in ascending order (first square a plain
+ *   product, later ones FMAs) and the G partials are combined by an xor-butterfly with
+ *   strides 1, 2, ..., G/2; chunk sums are added in ascending chunk order.
  * For F <= 2 (and F == 4 in fp32) this is the plain sequential FMA chain. */
 static inline Dt FN(row_norm)(const Dt* q, int64_t n, int norm_kind) {
   if (norm_kind == TODE_NORM_MAX) {
@@ -51,28 +52,34 @@ static inline Dt FN(row_norm)(const Dt* q, int64_t n, int norm_kind) {
   const int64_t N = n / VEC;
   int G = 1;
   while (G < 32 && G < N) G <<= 1;
-  Dt part[32], nxt[32];
-  for (int l = 0; l < G; ++l) {
-    Dt s = (Dt)0;
-    int first = 1;
-    for (int64_t j = l; j < N; j += G) {
-      for (int u = 0; u < VEC; ++u) {
-        const Dt v = q[j * VEC + u] / sqrt_f;
-        if (first) {
-          s = v * v;
-          first = 0;
-        } else {
-          s = DFMA(v, v, s);
+  const int64_t CHUNK = 1024; /* vectors per chunk = 32 per lane of a warp */
+  Dt total = (Dt)0;
+  for (int64_t c0 = 0; c0 < N; c0 += CHUNK) {
+    const int64_t c1 = c0 + CHUNK < N ? c0 + CHUNK : N;
+    Dt part[32], nxt[32];
+    for (int l = 0; l < G; ++l) {
+      Dt s = (Dt)0;
+      int first = 1;
+      for (int64_t j = c0 + l; j < c1; j += G) {
+        for (int u = 0; u < VEC; ++u) {
+          const Dt v = q[j * VEC + u] / sqrt_f;
+          if (first) {
+            s = v * v;
+            first = 0;
+          } else {
+            s = DFMA(v, v, s);
+          }
         }
       }
+      part[l] = s;
     }
-    part[l] = s;
+    for (int m = 1; m < G; m <<= 1) {
+      for (int l = 0; l < G; ++l) nxt[l] = part[l] + part[l ^ m];
+      for (int l = 0; l < G; ++l) part[l] = nxt[l];
+    }
+    total = c0 == 0 ? part[0] : total + part[0];
   }
-  for (int m = 1; m < G; m <<= 1) {
-    for (int l = 0; l < G; ++l) nxt[l] = part[l] + part[l ^ m];
-    for (int l = 0; l < G; ++l) part[l] = nxt[l];
-  }
-  return DSQRT(part[0]);
+  return DSQRT(total);
 }
 
 typedef struct FN(ctrl_out) {

@@ -1,0 +1,354 @@
+"""GPU kernel-level parity: every C-ABI op against the oracle's restatement of the same
+reference lines, bit-exact, over the feature-dimension geometries the kernels special-case
+(thread-per-sample, warp-per-sample with register cache, warp-per-sample streaming)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import torchode_b200 as to
+from oracle import driver
+from oracle import oracle as orc
+from torchode_b200 import _cabi, _launch
+from torchode_b200.single_step_methods import StepResult
+from torchode_b200.step_size_controllers import max_norm
+
+from helpers import bits_equal, ulps
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+NP = {"f32": np.float32, "f64": np.float64}
+DTYPES = [("f32", "f32"), ("f64", "f64"), ("f32", "f64"), ("f64", "f32")]
+FEATS = [1, 2, 3, 4, 6, 8, 256, 260, 1000]
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def rand_step(rng, B, F, D, T, n_stages=7):
+    y0 = rng.normal(size=(B, F)).astype(D)
+    ks = [rng.normal(size=(B, F)).astype(D) for _ in range(n_stages)]
+    dt = (rng.uniform(0.01, 0.2, size=B) * rng.choice([-1, 1], size=B)).astype(T)
+    return y0, ks, dt
+
+
+@pytest.mark.parametrize("dd,td", DTYPES)
+@pytest.mark.parametrize("F", FEATS)
+@pytest.mark.parametrize("method", [to.Dopri5, to.Tsit5])
+def test_stage_kernel(dd, td, F, method):
+    rng = np.random.default_rng(F * 7 + len(dd + td))
+    B = 37 if F > 8 else 1031
+    D, T = NP[dd], NP[td]
+    tab = method().to_cabi()
+    y0, ks, dt = rand_step(rng, B, F, D, T)
+    st = orc.HostState(y0, np.zeros(B, T), np.ones(B, T), None)
+    st.dt[:] = dt
+    st.running[::5] = 0  # finished rows are neither read nor written
+    for stage in range(1, 7):
+        want = orc.erk_stage(tab, stage, st, ks[:stage], np.full((B, F), 7.0, D))
+        out = torch.full((B, F), 7.0, dtype=cu(y0).dtype, device=DEV)
+        g = _launch.StagedState(to.InitialValueProblem(cu(y0), cu(np.zeros(B, T)), cu(np.ones(B, T))), 7, False)
+        g.dt.copy_(cu(dt))
+        g.running.copy_(cu(st.running))
+        kd = [cu(k) for k in ks[:stage]]
+        _cabi.check(_cabi.lib().tode_erk_stage(C.byref(tab), stage, C.byref(g.c), _launch.kptrs(kd),
+                                               out.data_ptr(), _launch.stream_ptr(out.device)), "stage")
+        assert bits_equal(out.cpu().numpy(), want), f"stage {stage}"
+
+
+@pytest.mark.parametrize("dd,td", DTYPES)
+@pytest.mark.parametrize("F", FEATS)
+@pytest.mark.parametrize("kind", ["integral", "pid", "pid_max_limits"])
+def test_adapt_step_size(dd, td, F, kind):
+    rng = np.random.default_rng(F + 100)
+    B = 29 if F > 8 else 517
+    D, T = NP[dd], NP[td]
+    tD = torch.from_numpy(np.zeros(1, D)).dtype
+    if kind == "integral":
+        ctrl = to.IntegralController(1e-6, 1e-3)
+    elif kind == "pid":
+        ctrl = to.PIDController(1e-7, 1e-5, 0.2, 0.5, 0.1)
+    else:
+        ctrl = to.PIDController(1e-4, 1e-3, 0.1, 0.6, 0.05, norm=max_norm, dt_min=0.02, dt_max=0.11,
+                                safety=0.8, factor_min=0.3, factor_max=4.0)
+    cab = ctrl.to_cabi(5, tD)
+    y0 = rng.normal(size=(B, F)).astype(D)
+    y1 = (y0 + 0.1 * rng.normal(size=(B, F))).astype(D)
+    err = (rng.normal(size=(B, F)) * 10.0 ** rng.uniform(-9, -2, size=(B, 1))).astype(D)
+    err[0] = 0.0           # zero error -> almost_zero floor -> factor_max (step_size_controllers_test.py:43-62)
+    err[1, 0] = np.inf     # -> INFINITE_NORM (:65-95)
+    y1[2, -1] = np.nan     # NaN state -> INFINITE_NORM (:98-122)
+    dt = (rng.uniform(0.01, 0.2, size=B) * rng.choice([-1, 1], size=B)).astype(T)
+    r1 = rng.uniform(0.1, 2.0, size=B).astype(D)
+    r2 = rng.uniform(0.1, 2.0, size=B).astype(D)
+    want = orc.adapt_step_size(cab, dt, y0, y1, err, r1, r2)
+
+    class S:
+        method_order, dt_min, dt_max = 5, None, None
+        prev_error_ratio, prev_prev_error_ratio = cu(r1), cu(r2)
+
+    accept, dt_next, r1o, r2o, status = _launch.adapt_step_size(ctrl, S, cu(dt), cu(y0), cu(y1), cu(err))
+    assert accept.cpu().numpy().tolist() == want["accept"].tolist()
+    assert bits_equal(dt_next.cpu().numpy(), want["dt_next"])
+    assert status.cpu().numpy().tolist() == want["status"].tolist()
+    if kind != "pid_max_limits":  # with dt_min, REACHED_DT_MIN may override (:419-422), as in the oracle
+        assert status[1].item() == to.Status.INFINITE_NORM.value
+        assert status[2].item() == to.Status.INFINITE_NORM.value
+    assert not accept[1] and not accept[2] and accept[0]
+    if kind != "integral":
+        assert bits_equal(r1o.cpu().numpy(), want["r1"]) and bits_equal(r2o.cpu().numpy(), want["r2"])
+
+
+@pytest.mark.parametrize("dd,td", DTYPES)
+@pytest.mark.parametrize("method", [to.Dopri5, to.Tsit5])
+def test_weighted_sum_time_nodes_interp(dd, td, method):
+    rng = np.random.default_rng(5)
+    B, F = 211, 5
+    D, T = NP[dd], NP[td]
+    m = method()
+    tab = m.to_cabi()
+    y0, ks, dt = rand_step(rng, B, F, D, T)
+    t0 = rng.normal(size=B).astype(T)
+    kd = [cu(k) for k in ks]
+    for which, name in ((_cabi.W_BERR, "b_err"), (_cabi.W_B, "b")):
+        want = orc.erk_weighted_sum(tab, which, dt, ks, y0 if name == "b" else None)
+        got = _launch.erk_weighted_sum(tab, name, cu(dt), kd, base=cu(y0) if name == "b" else None)
+        assert bits_equal(got.cpu().numpy(), want)
+    nodes = _launch.time_nodes(tab, cu(t0), cu(dt)).cpu().numpy()
+    c = np.array([tab.c[i] for i in range(7)]).astype(T)
+    assert np.abs(nodes - (t0[None] + c[:, None] * dt[None])).max() < 1e-5
+    # dense output at random points of random samples
+    N = 400
+    idx = rng.integers(0, B, size=N)
+    tq = (t0[idx] + rng.uniform(0, 1, size=N) * dt[idx]).astype(T)
+    y1 = (y0 + rng.normal(size=(B, F)) * 0.01).astype(D)
+    want = orc.interp_eval(tab, t0, dt, y0, y1, ks, tq, idx)
+    got = _launch.interp_eval(tab, cu(t0), cu(dt), cu(y0), cu(y1), torch.stack(kd), cu(tq), cu(idx))
+    assert bits_equal(got.cpu().numpy(), want)
+
+
+def _gpu_state_like(st, tab, ctrl_pid, t_eval=None, general=False):
+    prob = to.InitialValueProblem(cu(st.y), cu(st.t_start), cu(st.t_end), None if t_eval is None else cu(t_eval))
+    g = _launch.StagedState(prob, tab.n_stages, ctrl_pid, general=general)
+    for name in ("t", "dt", "y", "f0", "running", "n_steps", "n_accepted", "status", "cursor"):
+        getattr(g, name).copy_(cu(getattr(st, name)))
+    if ctrl_pid:
+        g.r1.copy_(cu(st.r1))
+        g.r2.copy_(cu(st.r2))
+    g.y_eval.copy_(cu(st.y_eval))
+    return g
+
+
+@pytest.mark.parametrize("dd,td", [("f32", "f32"), ("f64", "f64"), ("f32", "f64")])
+@pytest.mark.parametrize("F", [1, 2, 4, 12, 128, 256, 520, 3000])
+@pytest.mark.parametrize("with_t_eval", [False, True])
+def test_finish_kernel_one_iteration(dd, td, F, with_t_eval):
+    """One loop iteration on a random mid-solve state: every state array after tode_erk_finish
+    equals the oracle's (covers G=1, G=32 with register cache CI=1/2 and streaming CI=0)."""
+    rng = np.random.default_rng(F)
+    B = 300 if F <= 12 else 41
+    D, T = NP[dd], NP[td]
+    method, ctrl = to.Tsit5(), to.PIDController(1e-5, 1e-4, 0.2, 0.5, 0.05)
+    tab = method.to_cabi()
+    cab = ctrl.to_cabi(5, torch.from_numpy(np.zeros(1, D)).dtype, 50)
+    y0, ks, dt = rand_step(rng, B, F, D, T)
+    dt = np.abs(dt)
+    t_start = np.zeros(B, T)
+    t_end = rng.uniform(0.05, 1.0, size=B).astype(T)
+    t_eval = None
+    if with_t_eval:
+        t_eval = (t_end[:, None] * np.linspace(0, 1, 9)[None]).astype(T)
+    st = orc.HostState(y0, t_start, t_end, t_eval, pid=True)
+    st.t[:] = rng.uniform(0.0, 0.04, size=B).astype(T)
+    st.dt[:] = dt
+    st.f0[:] = ks[0]
+    st.r1[:] = rng.uniform(0.2, 1.5, size=B).astype(D)
+    st.r2[:] = rng.uniform(0.2, 1.5, size=B).astype(D)
+    st.n_steps[:] = rng.integers(0, 50, size=B)
+    st.n_accepted[:] = st.n_steps // 2
+    st.running[::7] = 0
+    st.cursor[:] = 1
+    st.y_eval[:] = 0
+    # small errors so that a good share of the steps is accepted: k ~ O(1), weights sum to 0
+    ks = [ks[0]] + [(ks[0] + 1e-3 * rng.normal(size=(B, F))).astype(D) for _ in range(6)]
+    y1 = (y0 + dt[:, None].astype(D) * ks[0]).astype(D)
+    g = _gpu_state_like(st, tab, True, t_eval)
+    orc.erk_finish(tab, cab, st, ks, y1)
+    kd = [g.f0] + [cu(k) for k in ks[1:]]
+    _cabi.check(_cabi.lib().tode_erk_finish(C.byref(tab), C.byref(cab), C.byref(g.c), _launch.kptrs(kd),
+                                            cu(y1).data_ptr(), _launch.stream_ptr(g.device)), "finish")
+    torch.cuda.synchronize()
+    assert 0.05 < st.n_accepted.sum() / max(1, st.n_steps.sum())  # the scenario exercises the commit
+    for name in ("t", "dt", "y", "f0", "r1", "r2", "running", "n_steps", "n_accepted", "status", "y_eval"):
+        assert bits_equal(getattr(g, name).cpu().numpy(), getattr(st, name)), name
+    if with_t_eval:
+        assert g.cursor.cpu().numpy().tolist() == st.cursor.tolist()
+    run = st.running.astype(bool)
+    assert bits_equal(g.t_nodes.cpu().numpy()[1:, run], st.t_nodes[1:, run])
+    ctl = g.ctl.cpu().numpy()
+    assert ctl[_cabi.CTL_ITERS] == 1 and ctl[_cabi.CTL_STOP] == st.ctl[_cabi.CTL_STOP]
+    assert ctl[_cabi.CTL_RUNNING] == 0 and ctl[_cabi.CTL_TICKET] == 0  # scratch words reset
+
+
+def heat_rhs_np(kappa):
+    def f(t, y):
+        out = np.zeros_like(y)
+        out[:, 1:-1] = y.dtype.type(kappa) * ((y[:, 2:] - y.dtype.type(2) * y[:, 1:-1]) + y[:, :-2])
+        return out
+    return f
+
+
+def heat_rhs_torch(kappa):
+    def f(t, y):
+        out = torch.zeros_like(y)
+        out[:, 1:-1] = kappa * ((y[:, 2:] - 2 * y[:, 1:-1]) + y[:, :-2])
+        return out
+    return f
+
+
+@pytest.mark.parametrize("N", [64, 1024, 4100])
+def test_staged_opaque_heat_equation_matches_oracle(N):
+    """Config C5 in miniature: method-of-lines heat equation (opaque stencil f), Tsit5 + I."""
+    rng = np.random.default_rng(N)
+    B = 6
+    x = np.linspace(0, 1, N, dtype=np.float32)
+    amp = rng.uniform(size=(B, 3)).astype(np.float32)
+    y0 = sum(amp[:, k - 1:k] * np.sin(np.float32(k * np.pi) * x)[None] for k in (1, 2, 3)).astype(np.float32)
+    kappa = 0.2 * (N - 1) ** 2 / 100.0  # keeps the spectral radius ~ 80: non-stiff
+    t0, t1 = np.zeros(B, np.float32), np.full(B, 0.5, np.float32)
+    method = to.Tsit5()
+    ctrl = to.IntegralController(1e-6, 1e-3)
+    want = driver.solve_opaque(heat_rhs_np(kappa), method.to_cabi(), ctrl.to_cabi(5, torch.float32), y0, t0, t1)
+    term = to.ODETerm(heat_rhs_torch(kappa))
+    solver = to.AutoDiffAdjoint(to.Tsit5(term), to.IntegralController(1e-6, 1e-3, term=term))
+    with torch.no_grad():
+        sol = solver.solve(to.InitialValueProblem(cu(y0), cu(t0), cu(t1)))
+    assert sol.stats["n_steps"].cpu().tolist() == want["n_steps"].tolist()
+    assert sol.stats["n_accepted"].cpu().tolist() == want["n_accepted"].tolist()
+    assert int(sol.stats["n_f_evals"][0]) == want["n_f_evals"]
+    assert sol.status.cpu().tolist() == want["status"].tolist()
+    assert bits_equal(sol.ys.cpu().numpy(), want["ys"])
+
+
+def test_general_mode_for_non_monotone_t_eval():
+    rng = np.random.default_rng(3)
+    B, F = 33, 2
+    y0 = (1 + rng.uniform(size=(B, F))).astype(np.float32)
+    t_eval = np.tile(np.linspace(0, 2, 9, dtype=np.float32), (B, 1))
+    t_eval[:, [2, 5]] = t_eval[:, [5, 2]]
+    t0, t1 = np.zeros(B, np.float32), np.full(B, 2.0, np.float32)
+    field = to.fields.LotkaVolterra()
+
+    def f_np(t, y):
+        x, z = y[:, 0], y[:, 1]
+        xz = x * z
+        return np.stack((np.float32(1.5) * x - np.float32(1.0) * xz, np.float32(1.0) * xz - np.float32(3.0) * z), 1)
+
+    want = driver.solve_opaque(f_np, to.Dopri5().to_cabi(), to.IntegralController(1e-6, 1e-3).to_cabi(5, torch.float32),
+                               y0, t0, t1, t_eval)
+    for f in (field, lambda t, y: field(t, y)):  # the fused route must hand over to the staged general mode
+        term = to.ODETerm(f)
+        solver = to.AutoDiffAdjoint(to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term))
+        with torch.no_grad():
+            sol = solver.solve(to.InitialValueProblem(cu(y0), cu(t0), cu(t1), cu(t_eval)))
+        assert sol.stats["n_steps"].cpu().tolist() == want["n_steps"].tolist()
+        assert sol.stats["n_initialized"].cpu().tolist() == want["n_initialized"].tolist()
+        assert bits_equal(sol.ys.cpu().numpy(), want["ys"])
+
+
+def test_protocol_step_and_custom_controller_route():
+    """Built-in Dopri5 under a foreign controller object: the generic loop calls Dopri5.step /
+    build_interpolation, which run the same CUDA kernels (stage, weighted sum, interp)."""
+    from torchode_b200.step_size_controllers import StepSizeController
+
+    class HalvingController(StepSizeController):
+        def init(self, term, problem, order, dt0, *, stats, args):
+            return torch.full_like(problem.t_start, 0.125), None, None
+
+        def adapt_step_size(self, t0, dt, y0, step_result, state, stats):
+            assert step_result.error_estimate is not None
+            return torch.ones_like(dt, dtype=torch.bool), dt, state, None
+
+        def merge_states(self, running, current, previous):
+            return current
+
+    B = 16
+    y0 = torch.linspace(1, 2, B, device=DEV)[:, None].repeat(1, 3)
+    t_eval = torch.linspace(0, 1, 5, device=DEV).repeat(B, 1)
+    term = to.ODETerm(lambda t, y: -0.5 * y)
+    solver = to.AutoDiffAdjoint(to.Dopri5(term), HalvingController())
+    with torch.no_grad():
+        sol = solver.solve(to.InitialValueProblem(y0, t_eval=t_eval))
+    assert sol.stats["n_steps"].tolist() == [8] * B and sol.stats["n_f_evals"].tolist() == [1 + 6 * 8] * B
+    want = y0[:, None, :] * torch.exp(-0.5 * t_eval)[:, :, None]
+    assert torch.allclose(sol.ys, want, rtol=1e-5)
+    # stand-alone protocol call: one step equals the oracle's ops
+    method = to.Dopri5(term)
+    prob = to.InitialValueProblem(y0, t_eval=t_eval)
+    stats = {}
+    term.init(prob, stats)
+    state = method.init(None, prob, None, stats=stats, args=None)
+    dt = torch.full((B,), 0.1, device=DEV)
+    res, interp_data, state2, status = method.step(None, None, y0, prob.t_start, dt, state, stats=stats, args=None)
+    assert status is None and isinstance(res, StepResult)
+    tab = method.to_cabi()
+    ks = [k.cpu().numpy() for k in interp_data.k]
+    err = orc.erk_error_estimate(tab, dt.cpu().numpy(), ks)
+    assert bits_equal(res.error_estimate.cpu().numpy(), err)
+    assert torch.equal(state2.prev_vf1, interp_data.k[-1])
+
+
+def test_fixed_step_controller_with_builtin_methods():
+    """fixed_step_controller_test.py:10-19: fixed steps vs the analytic solution (rel 1e-2)."""
+    B = 4
+    y0 = torch.ones(B, 2, device=DEV, dtype=torch.float64)
+    t_eval = torch.linspace(0, 2, 6, device=DEV, dtype=torch.float64).repeat(B, 1)
+    for method_cls in (to.Dopri5, to.Tsit5):
+        term = to.ODETerm(lambda t, y: -y)
+        solver = to.AutoDiffAdjoint(method_cls(term), to.FixedStepController())
+        with torch.no_grad():
+            sol = solver.solve(to.InitialValueProblem(y0, t_eval=t_eval),
+                               dt0=torch.full((B,), 0.05, device=DEV, dtype=torch.float64))
+        assert torch.allclose(sol.ys[:, :, 0], torch.exp(-t_eval), rtol=1e-2)
+        assert (sol.status == 0).all()
+
+
+def test_solve_ivp_default_matches_analytic_solution():
+    """interface_test.py:7-12: tsit5 + PID(1e-7) on y' = 2y/t + t^4 sin 2t - t^2 + 4t^3, rel 1e-5."""
+    def sol_fn(t):
+        return (-0.5 * t**4 * torch.cos(2 * t) + 0.5 * t**3 * torch.sin(2 * t) + 0.25 * t**2 * torch.cos(2 * t)
+                - t**3 + 2 * t**4 + (torch.pi - 0.25) * t**2)[..., None]
+
+    def dyn(t, y):
+        return (2 * y[:, 0] / t + t**4 * torch.sin(2 * t) - t**2 + 4 * t**3)[..., None]
+
+    t_eval = torch.tensor([[1.0, 1.5, 2.0, 3.0], [0.5, 1.0, 1.5, 2.5]], device=DEV, dtype=torch.float64)
+    with torch.no_grad():
+        sol = to.solve_ivp(dyn, sol_fn(t_eval[:, 0]), t_eval)
+    assert (sol.status == 0).all()
+    assert torch.allclose(sol.ys, sol_fn(t_eval), rtol=1e-5)
+
+
+def test_extra_args_reach_f_by_identity():
+    """extra_args_test.py:10-22."""
+    marker, seen = object(), []
+    term = to.ODETerm(lambda t, y, a: seen.append(a) or -y, with_args=True)
+    solver = to.AutoDiffAdjoint(to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term))
+    y0 = torch.ones(3, 2, device=DEV)
+    with torch.no_grad():
+        solver.solve(to.InitialValueProblem(y0, torch.zeros(3, device=DEV), torch.ones(3, device=DEV)), args=marker)
+    assert len(seen) >= 8 and all(a is marker for a in seen)
+
+
+def test_grad_requiring_inputs_are_refused_loudly():
+    lin = torch.nn.Linear(2, 2).to(DEV)
+    term = to.ODETerm(lambda t, y: lin(y))
+    term.lin = lin
+    solver = to.AutoDiffAdjoint(to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term))
+    prob = to.InitialValueProblem(torch.ones(3, 2, device=DEV), torch.zeros(3, device=DEV), torch.ones(3, device=DEV))
+    with pytest.raises(NotImplementedError, match="forward-only"):
+        solver.solve(prob)
+    with torch.no_grad():
+        assert (solver.solve(prob).status == 0).all()

@@ -17,6 +17,33 @@ namespace tode {
 constexpr int kBlock = 256;
 constexpr int kStages = TODE_MAX_STAGES;  // fused finish path is specialised for 7 stages
 
+// Resident CTAs per SM the finish kernel is compiled for (register budget 65536 / (256 n)).
+// Measured on B200 (profiles/r01_finish_occupancy.txt): the kernel is latency-bound at low
+// occupancy; fp32 thread-per-sample variants want 4 CTAs/SM (64 regs, a few spilled bytes),
+// fp64 ones 2 (more would spill the double-precision controller state), warp-per-sample
+// streaming variants 3.
+#ifndef TODE_FINISH_MINB_F32
+#define TODE_FINISH_MINB_F32 4
+#endif
+#ifndef TODE_FINISH_MINB_F32_V4
+#define TODE_FINISH_MINB_F32_V4 3
+#endif
+#ifndef TODE_FINISH_MINB_F64
+#define TODE_FINISH_MINB_F64 2
+#endif
+#ifndef TODE_FINISH_MINB_G32_F32
+#define TODE_FINISH_MINB_G32_F32 4
+#endif
+#ifndef TODE_FINISH_MINB_G32_F64
+#define TODE_FINISH_MINB_G32_F64 3
+#endif
+template <typename D, int G, int VEC>
+constexpr int finish_min_blocks() {
+  if (G == 32) return sizeof(D) == 8 ? TODE_FINISH_MINB_G32_F64 : TODE_FINISH_MINB_G32_F32;
+  if (sizeof(D) == 8) return TODE_FINISH_MINB_F64;
+  return VEC == 4 ? TODE_FINISH_MINB_F32_V4 : TODE_FINISH_MINB_F32;
+}
+
 // ---- vector load / store ------------------------------------------------------------
 template <typename D, int VEC>
 struct VecIO;
@@ -154,6 +181,8 @@ struct FinishArgs {
   const D* k[kStages];
   const D* y1;
   D sqrt_f;
+  D* scratch;  // split (multi-CTA per sample) mode: chunk partials + per-sample step records
+  long long scratch_elems;
 };
 
 // butterfly over the G lanes of a sample group (strides 1, 2, ..., G/2)
@@ -169,6 +198,48 @@ TODE_DEV D group_max(D v) {
   for (int m = 1; m < G; m <<= 1) v = max_nan(v, __shfl_xor_sync(0xffffffffu, v, m));
   return v;
 }
+
+// Per-sample norm over the row in the CANONICAL ORDER:
+// the row is cut into chunks of kChunkVec vectors (= 32 vectors per lane of a warp); inside a
+// chunk lane l sums the squares of its vectors in ascending order (first a product, then FMAs)
+// and the lane partials are combined by an xor-butterfly 1,2,4,...; chunk sums are added in
+// ascending chunk order.  Rows of up to kChunkVec vectors are a single chunk.
+// add() is called by the owning lane for each of its elements; slot_done() and result() must
+// be called by ALL lanes of the warp at the same points (they shuffle).
+constexpr int kChunkVec = 1024;
+template <typename D, int G>
+struct RowNorm {
+  D part, total, sqrt_f;
+  int cnt, kind;
+  bool first, first_chunk;
+  TODE_DEV RowNorm(int kind_, D sqrt_f_)
+      : part((D)0), total((D)0), sqrt_f(sqrt_f_), cnt(0), kind(kind_), first(true), first_chunk(true) {}
+  TODE_DEV void add(D q) {
+    if (kind == TODE_NORM_MAX) {
+      part = first ? fabs_(q) : max_nan(part, fabs_(q));
+      first = false;
+    } else {
+      sumsq_acc(part, first, fdiv(q, sqrt_f));
+    }
+  }
+  TODE_DEV void flush() {
+    const D c = group_sum<D, G>(part);
+    total = first_chunk ? c : tode::add(total, c);
+    first_chunk = false;
+    part = (D)0;
+    first = true;
+    cnt = 0;
+  }
+  // one vector slot per lane consumed (uniform across the warp)
+  TODE_DEV void slot_done() {
+    if (G == 32 && kind != TODE_NORM_MAX && ++cnt == kChunkVec / 32) flush();
+  }
+  TODE_DEV D result() {
+    if (kind == TODE_NORM_MAX) return group_max<D, G>(part);
+    if (cnt > 0 || first_chunk) flush();
+    return fsqrt(total);
+  }
+};
 
 // Block-wide accounting of (running samples, any failure) into the control block; the last
 // CTA to arrive evaluates `any(running) & all(status == 0)` (adjoints.py:186-190).
@@ -211,12 +282,64 @@ TODE_DEV void publish_termination(int* ctl, int my_running, int my_failed) {
   }
 }
 
-// G lanes per sample, VEC elements per vector, CI = number of vector chunks per lane kept in
-// registers between the reduction pass and the commit / dense-output pass (chunks beyond CI
-// are re-read; the cache is only ever indexed with compile-time constants).
-// NOTE: general (not_yet mask) mode relies on G == 1 or G == 32 (one sample per warp).
+// Per-sample decision of one loop iteration: controller + commit / running / status logic of
+// adjoints.py:150-181.  Shared by the single-launch finish kernel and the split-mode kernels.
+template <typename D, typename T>
+struct Decision {
+  CtrlOut<D, T> o;
+  T t_new, dir;
+  int status;
+  bool upd, running_new;
+};
+
+template <typename D, typename T>
+TODE_DEV Decision<D, T> decide_step(const CtrlP<D, T>& c, D nrm, T t0, T dt, T ts, T te, D r1, D r2,
+                                    int ns, bool act) {
+  Decision<D, T> d;
+  d.o = controller<D, T>(c, nrm, dt, r1, r2);
+  d.upd = d.o.accept && act;            // adjoints.py:150
+  d.t_new = d.upd ? add(t0, dt) : t0;   // :151
+  d.dir = dir_of(ts, te);
+  d.running_new = act && (ffma(d.dir, d.t_new, mul(-d.dir, te)) < (T)0);  // :169
+  d.status = d.o.status;                                                  // :171-181
+  if (c.max_steps >= 0 && (long long)ns >= c.max_steps) d.status = TODE_REACHED_MAX_STEPS;
+  return d;
+}
+
+// Writes the per-sample scalars of a running sample after its iteration (one thread per sample).
+template <typename D, typename T>
+TODE_DEV void store_sample_scalars(const FinishArgs<D, T>& A, long long b, const Decision<D, T>& d, T dt,
+                                   T ts, T te, int ns, int cur, int& my_running, int& my_failed) {
+  const T t_min = ts < te ? ts : te;  // adjoints.py:66-67
+  const T t_max = ts < te ? te : ts;
+  T dt_new = d.running_new ? d.o.dt_next : dt;                           // :247
+  dt_new = clamp_nan(dt_new, sub(t_min, d.t_new), sub(t_max, d.t_new));  // :251
+  A.t[b] = d.t_new;
+  A.dt[b] = dt_new;
+  A.n_steps[b] = ns;
+  if (d.upd) A.n_accepted[b] += 1;
+  A.status[b] = d.status;
+  A.running[b] = (uint8_t)d.running_new;
+  if (A.ctrl.pid && d.running_new) {  // PIDController.merge_states :639-647
+    A.r1[b] = d.o.r1;
+    A.r2[b] = d.o.r2;
+  }
+  if (A.Tn > 0 && A.not_yet == nullptr) A.cursor[b] = cur;
+  if (A.t_nodes != nullptr) {
+#pragma unroll
+    for (int i = 1; i < kStages; ++i) A.t_nodes[(long long)i * A.B + b] = ffma(A.tab.c[i], dt_new, d.t_new);
+  }
+  my_running += d.running_new ? 1 : 0;
+  my_failed |= (d.status != TODE_SUCCESS) ? 1 : 0;
+}
+
+// G lanes per sample, VEC elements per vector, CI = number of vector chunks per lane whose
+// commit operands (y1, k[S-1]) are kept in registers between the reduction pass and the commit
+// (chunks beyond CI are re-read; the cache is only ever indexed with compile-time constants).
+// NOTE: general (not_yet mask) mode requires G == 1 or G == 32 (one sample per warp); the
+// launcher routes 1 < G < 32 problems in mask mode to the G == 32 instantiation (same bits).
 template <typename D, typename T, int G, int VEC, int CI>
-__global__ void __launch_bounds__(kBlock) erk_finish_kernel(const __grid_constant__ FinishArgs<D, T> A) {
+__global__ void __launch_bounds__(kBlock, finish_min_blocks<D, G, VEC>()) erk_finish_kernel(const __grid_constant__ FinishArgs<D, T> A) {
   if (A.ctl[TODE_CTL_STOP]) return;
   constexpr int S = kStages;
   constexpr int CC = CI > 0 ? CI : 1;
@@ -254,9 +377,10 @@ __global__ void __launch_bounds__(kBlock) erk_finish_kernel(const __grid_constan
     const long long row = b * A.F;
 
     // ---- pass 1: error estimate, bounds, per-sample norm (step_size_controllers.py:394-400)
-    D y0c[CC][VEC], y1c[CC][VEC], kc[CC][S][VEC];
-    D part = (D)0;
-    bool first = true;
+    // Only the two rows the commit needs (y1, k[S-1]) stay in registers (CI chunks per lane);
+    // the dense output re-reads its operands, which were just loaded by the same lane (L1/L2).
+    D y1c[CC][VEC], k6c[CC][VEC];
+    RowNorm<D, G> rn(c.norm, A.sqrt_f);
     auto load_chunk = [&](long long it, D(&y0v)[VEC], D(&y1v)[VEC], D(&kv)[S][VEC]) {
       const long long e = row + (lane + it * G) * VEC;
       VecIO<D, VEC>::ld(A.y + e, y0v);
@@ -272,22 +396,21 @@ __global__ void __launch_bounds__(kBlock) erk_finish_kernel(const __grid_constan
         for (int s = 0; s < S; ++s) ks[s] = kv[s][x];
         const D err = weighted_sum<D, S>(dtD, tab.b_err, ks);  // runge_kutta.py:269
         const D bounds = ffma(c.rtol, max_nan(fabs_(y0v[x]), fabs_(y1v[x])), c.atol);
-        const D q = fdiv(fabs_(err), bounds);
-        if (c.norm == TODE_NORM_MAX) {
-          part = first ? q : max_nan(part, q);
-          first = false;
-        } else {
-          sumsq_acc(part, first, fdiv(q, A.sqrt_f));
-        }
+        rn.add(fdiv(fabs_(err), bounds));
       }
     };
     if (CI > 0) {
 #pragma unroll
-      for (int ci = 0; ci < CC; ++ci)
+      for (int ci = 0; ci < CC; ++ci) {
         if (act && lane + (long long)ci * G < n) {
-          load_chunk(ci, y0c[ci], y1c[ci], kc[ci]);
-          reduce_chunk(y0c[ci], y1c[ci], kc[ci]);
+          D y0v[VEC], kv[S][VEC];
+          load_chunk(ci, y0v, y1c[ci], kv);
+          reduce_chunk(y0v, y1c[ci], kv);
+#pragma unroll
+          for (int x = 0; x < VEC; ++x) k6c[ci][x] = kv[S - 1][x];
         }
+        rn.slot_done();
+      }
     }
     for (long long it = CI; it < n_it; ++it) {
       if (act && lane + it * G < n) {
@@ -295,22 +418,15 @@ __global__ void __launch_bounds__(kBlock) erk_finish_kernel(const __grid_constan
         load_chunk(it, y0v, y1v, kv);
         reduce_chunk(y0v, y1v, kv);
       }
+      rn.slot_done();
     }
-    D nrm;
-    if (c.norm == TODE_NORM_MAX) {
-      nrm = group_max<D, G>(part);
-    } else {
-      nrm = fsqrt(group_sum<D, G>(part));
-    }
+    const D nrm = rn.result();
 
     // ---- controller, commit decision (all lanes of the group, redundantly) --------------
-    const CtrlOut<D, T> o = controller<D, T>(c, nrm, dt, r1, r2);
-    const bool upd = o.accept && act;        // adjoints.py:150
-    const T t_new = upd ? add(t0, dt) : t0;  // :151
-    const T dir = dir_of(ts, te);
-    const bool running_new = act && (ffma(dir, t_new, mul(-dir, te)) < (T)0);  // :169
-    int status = o.status;                                                    // :171-181
-    if (c.max_steps >= 0 && (long long)ns >= c.max_steps) status = TODE_REACHED_MAX_STEPS;
+    const Decision<D, T> d = decide_step<D, T>(c, nrm, t0, dt, ts, te, r1, r2, ns, act);
+    const bool upd = d.upd, running_new = d.running_new;
+    const T t_new = d.t_new, dir = d.dir;
+    const int status = d.status;
 
     // ---- dense output with the data of THIS step (adjoints.py:215-234, 298-301) ---------
     auto eval_chunk = [&](long long it, const D(&y0v)[VEC], const D(&y1v)[VEC],
@@ -328,12 +444,7 @@ __global__ void __launch_bounds__(kBlock) erk_finish_kernel(const __grid_constan
     };
     auto eval_point = [&](T tq, D* dst_row) {
       const D x = interp_x<D, T>(tq, t0, dt);
-      if (CI > 0) {
-#pragma unroll
-        for (int ci = 0; ci < CC; ++ci)
-          if (lane + (long long)ci * G < n) eval_chunk(ci, y0c[ci], y1c[ci], kc[ci], x, dst_row);
-      }
-      for (long long it = CI; it < n_it; ++it) {
+      for (long long it = 0; it < n_it; ++it) {
         if (lane + it * G < n) {
           D y0v[VEC], y1v[VEC], kv[S][VEC];
           load_chunk(it, y0v, y1v, kv);
@@ -382,7 +493,7 @@ __global__ void __launch_bounds__(kBlock) erk_finish_kernel(const __grid_constan
           if (lane + (long long)ci * G < n) {
             const long long e = row + (lane + (long long)ci * G) * VEC;
             VecIO<D, VEC>::st(A.y + e, y1c[ci]);
-            VecIO<D, VEC>::st(A.f0 + e, kc[ci][S - 1]);
+            VecIO<D, VEC>::st(A.f0 + e, k6c[ci]);
           }
       }
       for (long long it = CI; it < n_it; ++it) {
@@ -399,29 +510,7 @@ __global__ void __launch_bounds__(kBlock) erk_finish_kernel(const __grid_constan
 
     // ---- per-sample scalars (lane 0 of the group) ---------------------------------------
     if (G > 1) __syncwarp();
-    if (act && lane == 0) {
-      const T t_min = ts < te ? ts : te;  // adjoints.py:66-67
-      const T t_max = ts < te ? te : ts;
-      T dt_new = running_new ? o.dt_next : dt;                           // :247
-      dt_new = clamp_nan(dt_new, sub(t_min, t_new), sub(t_max, t_new));  // :251
-      A.t[b] = t_new;
-      A.dt[b] = dt_new;
-      A.n_steps[b] = ns;
-      if (upd) A.n_accepted[b] += 1;
-      A.status[b] = status;
-      A.running[b] = (uint8_t)running_new;
-      if (c.pid && running_new) {  // PIDController.merge_states :639-647
-        A.r1[b] = o.r1;
-        A.r2[b] = o.r2;
-      }
-      if (A.Tn > 0 && A.not_yet == nullptr) A.cursor[b] = cur;
-      if (A.t_nodes != nullptr) {
-#pragma unroll
-        for (int i = 1; i < S; ++i) A.t_nodes[(long long)i * A.B + b] = ffma(tab.c[i], dt_new, t_new);
-      }
-      my_running += running_new ? 1 : 0;
-      my_failed |= (status != TODE_SUCCESS) ? 1 : 0;
-    }
+    if (act && lane == 0) store_sample_scalars<D, T>(A, b, d, dt, ts, te, ns, cur, my_running, my_failed);
   }
   publish_termination(A.ctl, my_running, my_failed);
 }
@@ -461,21 +550,6 @@ struct InitArgs {
   D sqrt_f;
 };
 
-template <typename D, int G>
-TODE_DEV D finish_norm(D part, int norm_kind) {
-  if (norm_kind == TODE_NORM_MAX) return group_max<D, G>(part);
-  return fsqrt(group_sum<D, G>(part));
-}
-template <typename D>
-TODE_DEV void norm_acc(D& part, bool& first, D q, int norm_kind, D sqrt_f) {
-  if (norm_kind == TODE_NORM_MAX) {
-    part = first ? fabs_(q) : max_nan(part, fabs_(q));
-    first = false;
-  } else {
-    sumsq_acc(part, first, fdiv(q, sqrt_f));
-  }
-}
-
 // part a: d0, d1, dt0, y1 = y0 + dir*dt0*f0, t1 = t0 + dir*dt0   (:459-479)
 template <typename D, typename T, int G, int VEC>
 __global__ void __launch_bounds__(kBlock) init_step_a_kernel(const __grid_constant__ InitArgs<D, T> A) {
@@ -488,8 +562,7 @@ __global__ void __launch_bounds__(kBlock) init_step_a_kernel(const __grid_consta
     const long long b = base + threadIdx.x / G;
     const bool act = b < A.B;
     const long long row = b * A.F;
-    D p0 = (D)0, p1 = (D)0;
-    bool f0first = true, f1first = true;
+    RowNorm<D, G> n0(c.norm, A.sqrt_f), n1(c.norm, A.sqrt_f);
     for (long long it = 0; it < n_it; ++it) {
       const long long j = lane + it * G;
       if (act && j < n) {
@@ -499,13 +572,15 @@ __global__ void __launch_bounds__(kBlock) init_step_a_kernel(const __grid_consta
 #pragma unroll
         for (int x = 0; x < VEC; ++x) {
           const D inv = fdiv((D)1, ffma(c.rtol, fabs_(yv[x]), c.atol));  // :461-462
-          norm_acc(p0, f0first, mul(yv[x], inv), c.norm, A.sqrt_f);      // :464
-          norm_acc(p1, f1first, mul(fv[x], inv), c.norm, A.sqrt_f);      // :465
+          n0.add(mul(yv[x], inv));                                       // :464
+          n1.add(mul(fv[x], inv));                                       // :465
         }
       }
+      n0.slot_done();
+      n1.slot_done();
     }
-    const D d0 = finish_norm<D, G>(p0, c.norm);
-    const D d1 = finish_norm<D, G>(p1, c.norm);
+    const D d0 = n0.result();
+    const D d1 = n1.result();
     T ts = (T)0, te = (T)0;
     if (act) {
       ts = A.t_start[b];
@@ -557,8 +632,7 @@ __global__ void __launch_bounds__(kBlock) init_step_b_kernel(const __grid_consta
     const T dir = dir_of(ts, te);
     T dt = (T)0;
     if (A.f1 != nullptr) {
-      D p2 = (D)0;
-      bool first = true;
+      RowNorm<D, G> n2(c.norm, A.sqrt_f);
       for (long long it = 0; it < n_it; ++it) {
         const long long j = lane + it * G;
         if (act && j < n) {
@@ -569,11 +643,12 @@ __global__ void __launch_bounds__(kBlock) init_step_b_kernel(const __grid_consta
 #pragma unroll
           for (int x = 0; x < VEC; ++x) {
             const D inv = fdiv((D)1, ffma(c.rtol, fabs_(yv[x]), c.atol));
-            norm_acc(p2, first, mul(sub(f1v[x], f0v[x]), inv), c.norm, A.sqrt_f);
+            n2.add(mul(sub(f1v[x], f0v[x]), inv));
           }
         }
+        n2.slot_done();
       }
-      const D nrm2 = finish_norm<D, G>(p2, c.norm);
+      const D nrm2 = n2.result();
       D dt0 = (D)0, d1 = (D)0;
       if (act) {
         dt0 = A.scratch[b];

@@ -5,69 +5,9 @@
 
 namespace tode {
 
-template <typename D, typename T, int G, int VEC, int CI>
-static int launch_finish_cfg(const FinishArgs<D, T>& a, cudaStream_t stream) {
-  const long long gpb = kBlock / G;
-  // persistent-style grid: few CTAs -> few termination atomics; 8 resident CTAs / SM
-  const unsigned grid = grid_for(a.B, gpb, 8);
-  erk_finish_kernel<D, T, G, VEC, CI><<<grid, kBlock, 0, stream>>>(a);
-  return launch_status();
-}
-
-template <typename D, typename T, int VEC>
-static int launch_finish_vec(const FinishArgs<D, T>& a, cudaStream_t stream) {
-  const long long n = a.F / VEC;
-  if (geom_lanes(n) == 1) return launch_finish_cfg<D, T, 1, VEC, 1>(a, stream);
-  if (n <= 32) return launch_finish_cfg<D, T, 32, VEC, 1>(a, stream);
-  if (n <= 64) return launch_finish_cfg<D, T, 32, VEC, 2>(a, stream);
-  return launch_finish_cfg<D, T, 32, VEC, 0>(a, stream);
-}
-
 template <typename D, typename T>
-static int launch_finish(const tode_tableau* tab, const tode_controller* ctrl, const tode_state* st,
-                         const void* const* k, const void* y1, cudaStream_t stream) {
-  if (tab->n_stages != kStages) return TODE_ENOSUP;
-  const int vec = geom_vec<D>(st->F);
-  const size_t al = sizeof(D) * vec;
-  if (!aligned_to(st->y, al) || !aligned_to(st->f0, al) || !aligned_to(y1, al) ||
-      !aligned_to(st->y_eval, al))
-    return TODE_EALIGN;
-  FinishArgs<D, T> a{};
-  a.tab = make_tab<D, T>(tab);
-  a.ctrl = make_ctrl<D, T>(ctrl);
-  a.B = st->B;
-  a.F = st->F;
-  a.Tn = st->T;
-  a.t_start = static_cast<const T*>(st->t_start);
-  a.t_end = static_cast<const T*>(st->t_end);
-  a.t_eval = static_cast<const T*>(st->t_eval);
-  a.te_stride = st->t_eval_stride_b;
-  a.t = static_cast<T*>(st->t);
-  a.dt = static_cast<T*>(st->dt);
-  a.y = static_cast<D*>(st->y);
-  a.f0 = static_cast<D*>(st->f0);
-  a.r1 = static_cast<D*>(st->r1);
-  a.r2 = static_cast<D*>(st->r2);
-  a.running = st->running;
-  a.n_steps = st->n_steps;
-  a.n_accepted = st->n_accepted;
-  a.status = st->status;
-  a.cursor = st->cursor;
-  a.not_yet = st->not_yet;
-  a.y_eval = static_cast<D*>(st->y_eval);
-  a.t_nodes = static_cast<T*>(st->t_nodes);
-  a.ctl = st->ctl;
-  for (int s = 0; s < kStages; ++s) {
-    if (!aligned_to(k[s], al)) return TODE_EALIGN;
-    a.k[s] = static_cast<const D*>(k[s]);
-  }
-  a.y1 = static_cast<const D*>(y1);
-  a.sqrt_f = (D)std::sqrt((double)st->F);
-  if (a.B == 0) return 0;
-  if (sizeof(D) == 4 && vec == 4) return launch_finish_vec<D, T, (sizeof(D) == 4 ? 4 : 2)>(a, stream);
-  if (vec == 2) return launch_finish_vec<D, T, 2>(a, stream);
-  return launch_finish_vec<D, T, 1>(a, stream);
-}
+int launch_finish(const tode_tableau* tab, const tode_controller* ctrl, const tode_state* st,
+                  const void* const* k, const void* y1, cudaStream_t stream);
 
 // ---- stand-alone controller op (step_size_controllers.py:393-429 / 738-774) --------------
 template <typename D, typename T>
@@ -100,8 +40,7 @@ __global__ void __launch_bounds__(kBlock) adapt_kernel(const __grid_constant__ A
     const long long b = base + threadIdx.x / G;
     const bool act = b < A.B;
     const long long row = b * A.F;
-    D part = (D)0;
-    bool first = true;
+    RowNorm<D, G> rn(c.norm, A.sqrt_f);
     for (long long it = 0; it < n_it; ++it) {
       const long long j = lane + it * G;
       if (act && j < n) {
@@ -112,11 +51,12 @@ __global__ void __launch_bounds__(kBlock) adapt_kernel(const __grid_constant__ A
 #pragma unroll
         for (int x = 0; x < VEC; ++x) {
           const D bounds = ffma(c.rtol, max_nan(fabs_(y0v[x]), fabs_(y1v[x])), c.atol);
-          norm_acc(part, first, fdiv(fabs_(ev[x]), bounds), c.norm, A.sqrt_f);
+          rn.add(fdiv(fabs_(ev[x]), bounds));
         }
       }
+      rn.slot_done();
     }
-    const D nrm = finish_norm<D, G>(part, c.norm);
+    const D nrm = rn.result();
     if (act && lane == 0) {
       const D r1 = A.r1 != nullptr ? A.r1[b] : (D)1;
       const D r2 = A.r2 != nullptr ? A.r2[b] : (D)1;

@@ -1,0 +1,6 @@
+// explicit instantiation of the finish launcher for data=float, time=double
+#include "finish_impl.cuh"
+namespace tode {
+template int launch_finish<float, double>(const tode_tableau*, const tode_controller*, const tode_state*,
+                                     const void* const*, const void*, cudaStream_t);
+}

@@ -27,8 +27,8 @@ static int launch_fused(int field, const double* fp, const tode_tableau* tab, co
                         const tode_problem* prob, const tode_solution* sol, int64_t iter_cap,
                         cudaStream_t stream) {
   if (tab->n_stages != kStagesFused) return TODE_ENOSUP;
-  const size_t row_bytes = sizeof(D) * prob->F;
-  const size_t al = row_bytes >= 16 ? 16 : row_bytes;
+  // load_row / store_row use one vector access per row for F == 2 (and F == 4 in fp32)
+  const size_t al = prob->F == 2 ? 2 * sizeof(D) : ((prob->F == 4 && sizeof(D) == 4) ? 16 : sizeof(D));
   if (!aligned_to(prob->y0, al) || !aligned_to(sol->ys, al)) return TODE_EALIGN;
   FusedArgs<D, T> a{};
   a.tab = make_tab<D, T>(tab);
