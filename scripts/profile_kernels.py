@@ -14,7 +14,8 @@ if __name__ == "__main__":
         shapes = {"path_a": [(1 << 24, 2, torch.float32)],
                   "path_a_all": [(1 << 24, 2, torch.float32), (1 << 23, 2, torch.float64),
                                  (1 << 18, 256, torch.float32), (1 << 17, 256, torch.float64),
-                                 (1 << 22, 8, torch.float32), (1 << 14, 4096, torch.float32)]}[which]
+                                 (1 << 22, 8, torch.float32), (1 << 14, 4096, torch.float32),
+                                 (64, 1 << 20, torch.float32)]}[which]
         for B, F, dt in shapes:
             for r in bench.measure_path_a_kernels(dev, bench.peaks()[0], reps=3, B=B, F=F, dtype=dt):
                 print(f"{r['kernel']:55s} {r['ms']:8.4f} ms {r['achieved']:8.1f} GB/s frac {r['frac']:.3f}"

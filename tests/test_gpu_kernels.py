@@ -142,11 +142,12 @@ def _gpu_state_like(st, tab, ctrl_pid, t_eval=None, general=False):
 
 
 @pytest.mark.parametrize("dd,td", [("f32", "f32"), ("f64", "f64"), ("f32", "f64")])
-@pytest.mark.parametrize("F", [1, 2, 4, 12, 128, 256, 520, 3000])
+@pytest.mark.parametrize("F", [1, 2, 4, 12, 128, 256, 520, 3000, 9000])
 @pytest.mark.parametrize("with_t_eval", [False, True])
 def test_finish_kernel_one_iteration(dd, td, F, with_t_eval):
     """One loop iteration on a random mid-solve state: every state array after tode_erk_finish
-    equals the oracle's (covers G=1, G=32 with register cache CI=1/2 and streaming CI=0)."""
+    equals the oracle's (covers the thread-per-sample, lane-group, warp-per-sample streaming and
+    -- F = 9000 -- the three-launch split-mode variants of the finish kernel)."""
     rng = np.random.default_rng(F)
     B = 300 if F <= 12 else 41
     D, T = NP[dd], NP[td]
@@ -208,7 +209,7 @@ def heat_rhs_torch(kappa):
     return f
 
 
-@pytest.mark.parametrize("N", [64, 1024, 4100])
+@pytest.mark.parametrize("N", [64, 1024, 4100, 16384])
 def test_staged_opaque_heat_equation_matches_oracle(N):
     """Config C5 in miniature: method-of-lines heat equation (opaque stencil f), Tsit5 + I."""
     rng = np.random.default_rng(N)
@@ -352,3 +353,22 @@ def test_grad_requiring_inputs_are_refused_loudly():
         solver.solve(prob)
     with torch.no_grad():
         assert (solver.solve(prob).status == 0).all()
+
+
+def test_cuda_graph_replay_of_the_staged_iteration_is_bit_identical():
+    rng = np.random.default_rng(11)
+    B = 257
+    y0 = cu((1 + rng.uniform(size=(B, 2))).astype(np.float32))
+    t_eval = torch.linspace(0, 5, 20, device=DEV).expand(B, 20)
+    field = to.fields.LotkaVolterra()
+    sols = []
+    for use_graph in (False, True):
+        term = to.ODETerm(lambda t, y: field(t, y))
+        solver = to.AutoDiffAdjoint(to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term))
+        solver.use_cuda_graph = use_graph
+        with torch.no_grad():
+            sols.append(solver.solve(to.InitialValueProblem(y0, t_eval=t_eval)))
+    a, b = sols
+    assert torch.equal(a.ys, b.ys) and torch.equal(a.stats["n_steps"], b.stats["n_steps"])
+    assert torch.equal(a.stats["n_accepted"], b.stats["n_accepted"]) and torch.equal(a.status, b.status)
+    assert a.stats["n_f_evals"].tolist() == b.stats["n_f_evals"].tolist()

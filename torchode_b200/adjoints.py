@@ -43,6 +43,12 @@ class AutoDiffAdjoint(nn.Module):
         self.backprop_through_step_size_control = backprop_through_step_size_control
         #: how many loop iterations the host may run ahead of the device (staged route)
         self.lookahead = 3
+        #: staged route: capture one loop iteration (6 x (stage kernel, f) + finish kernel) into a
+        #: CUDA graph after the first, eagerly launched iteration and replay it.  Opt-in, because
+        #: the Python body of ``f`` then runs only once more (at capture): ``f`` must be
+        #: capturable (no host sync, no data-dependent Python control flow) and free of host side
+        #: effects.  Removes the launch latency that dominates small problems.
+        self.use_cuda_graph = False
 
     # ------------------------------------------------------------------------------------
     def _kernel_route(self) -> bool:
@@ -187,9 +193,8 @@ class AutoDiffAdjoint(nn.Module):
         ks = [st.f0] + [None] * (S - 1)
         stage, finish = lib.tode_erk_stage, lib.tode_erk_finish
         y_stage, t_nodes = st.y_stage, st.t_nodes
-        launched = 0
-        ctl_host = None
-        while True:
+
+        def launch_iteration(stream):
             for i in range(1, S):
                 y_i = y_stage[i - 1]
                 rc = stage(tab_p, i, st_p, kp, y_i.data_ptr(), stream)
@@ -201,6 +206,17 @@ class AutoDiffAdjoint(nn.Module):
             rc = finish(tab_p, ctrl_p, st_p, kp, y_stage[S - 2].data_ptr(), stream)
             if rc:
                 _cabi.check(rc, "tode_erk_finish")
+
+        launched = 0
+        ctl_host = None
+        graph = None
+        while True:
+            if graph is not None:
+                graph.replay()
+            else:
+                launch_iteration(stream)
+                if self.use_cuda_graph and launched == 0:
+                    graph = self._capture_iteration(launch_iteration, dev)
             slot = launched % (look + 1)
             pinned[slot].copy_(st.ctl, non_blocking=True)
             events[slot].record()
@@ -234,6 +250,17 @@ class AutoDiffAdjoint(nn.Module):
             stats["n_initialized"] = torch.ones(B, dtype=torch.long, device=dev)
             ts = problem.t_end[:, None]
         return Solution(ts=ts, ys=st.y_eval, stats=stats, status=st.status.to(torch.long))
+
+    @staticmethod
+    def _capture_iteration(launch_iteration, dev):
+        """Record one loop iteration into a CUDA graph: inside the capture torch's current stream
+        is the capturing side stream, so the kernels launched through the C-ABI are handed that
+        stream; f's outputs live in the graph's private memory pool (static addresses)."""
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.current_stream(dev).synchronize()
+        with torch.cuda.graph(graph):
+            launch_iteration(_launch.stream_ptr(dev))
+        return graph
 
     # ------------------------------------------------------------------------------------
     # route 3: foreign plug-ins (the reference's operator API)

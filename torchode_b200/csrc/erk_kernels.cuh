@@ -26,7 +26,7 @@ constexpr int kStages = TODE_MAX_STAGES;  // fused finish path is specialised fo
 #define TODE_FINISH_MINB_F32 4
 #endif
 #ifndef TODE_FINISH_MINB_F32_V4
-#define TODE_FINISH_MINB_F32_V4 3
+#define TODE_FINISH_MINB_F32_V4 4
 #endif
 #ifndef TODE_FINISH_MINB_F64
 #define TODE_FINISH_MINB_F64 2

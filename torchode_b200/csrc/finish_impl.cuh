@@ -3,6 +3,7 @@
 #pragma once
 #include "api_common.cuh"
 #include "erk_kernels.cuh"
+#include "erk_finish_split.cuh"
 
 namespace tode {
 
@@ -15,8 +16,25 @@ static int launch_finish_cfg(const FinishArgs<D, T>& a, cudaStream_t stream) {
   return launch_status();
 }
 
+// few samples x huge rows: one warp per (sample, chunk), three launches (erk_finish_split.cuh)
+template <typename D, typename T, int VEC>
+static int launch_finish_split(const FinishArgs<D, T>& a, cudaStream_t stream) {
+  const long long n = a.F / VEC;
+  const long long cpr = (n + kChunkVec - 1) / kChunkVec;
+  const long long need = a.B * cpr + (a.B * (long long)sizeof(SplitAux<T>) + 32) / (long long)sizeof(D) + 8;
+  if (a.scratch == nullptr || a.scratch_elems < need) return TODE_EINVAL;
+  const unsigned grid = grid_for(a.B * cpr, kBlock / 32, 8);
+  finish_split_partial_kernel<D, T, VEC><<<grid, kBlock, 0, stream>>>(a);
+  finish_split_control_kernel<D, T><<<grid_for(a.B, kBlock, 1), kBlock, 0, stream>>>(a, cpr);
+  finish_split_commit_kernel<D, T, VEC><<<grid, kBlock, 0, stream>>>(a);
+  return launch_status();
+}
+
 template <typename D, typename T, int VEC>
 static int launch_finish_vec(const FinishArgs<D, T>& a, cudaStream_t stream) {
+  // warp-per-sample cannot fill the machine with few, very long rows
+  if (a.not_yet == nullptr && a.F / VEC >= 2 * kChunkVec && a.B < 16LL * sm_count())
+    return launch_finish_split<D, T, VEC>(a, stream);
   // lane-group size of the canonical geometry; groups of 1..16 lanes keep the 9 rows in
   // registers (one chunk per lane), warp-per-sample streams (re-reads hit L1/L2)
   int g = geom_lanes(a.F / VEC);
@@ -71,6 +89,8 @@ int launch_finish(const tode_tableau* tab, const tode_controller* ctrl, const to
   }
   a.y1 = static_cast<const D*>(y1);
   a.sqrt_f = (D)std::sqrt((double)st->F);
+  a.scratch = static_cast<D*>(st->scratch);
+  a.scratch_elems = st->scratch_elems;
   if (a.B == 0) return 0;
   if (sizeof(D) == 4 && vec == 4) return launch_finish_vec<D, T, (sizeof(D) == 4 ? 4 : 2)>(a, stream);
   if (vec == 2) return launch_finish_vec<D, T, 2>(a, stream);
