@@ -92,6 +92,10 @@ if __name__ == "__main__":
             c2(1 << 16)
             c2(1 << 20)
             c3(1 << 20)
+        if which == "fusedonly":
+            c2(1 << 20)
+            c3(1 << 20)
+            sys.exit(0)
         for GRAPH in (False, True):
             c2(1 << 10, staged=True)
             c2(1 << 14, staged=True)

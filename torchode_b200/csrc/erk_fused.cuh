@@ -110,8 +110,9 @@ TODE_DEV void store_row(D* p, const D* r) {
   }
 }
 
-template <typename D, typename T, int F, int FIELD>
-__global__ void __launch_bounds__(128) solve_fused_kernel(const __grid_constant__ FusedArgs<D, T> A) {
+// MINB = resident CTAs per SM the kernel is compiled for (register budget 65536 / (128 MINB))
+template <typename D, typename T, int F, int FIELD, int MINB>
+__global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_constant__ FusedArgs<D, T> A) {
   constexpr int S = kStagesFused;
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = b < A.B;

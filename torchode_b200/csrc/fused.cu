@@ -1,5 +1,6 @@
 // C-ABI: tode_solve_fused -- whole solve of a built-in analytic field in one launch.
 #include <climits>
+#include <cstdlib>
 
 #include "api_common.cuh"
 #include "erk_fused.cuh"
@@ -13,12 +14,29 @@ __global__ void summary_init_kernel(int* summary) {
   summary[3] = 0;
 }
 
+#ifndef TODE_FUSED_MINB
+#define TODE_FUSED_MINB 4
+#endif
+
 template <typename D, typename T, int F, int FIELD>
 static int launch_fused_f(const FusedArgs<D, T>& a, cudaStream_t stream) {
   constexpr int kThreads = 128;
   summary_init_kernel<<<1, 1, 0, stream>>>(a.summary);
   const unsigned grid = (unsigned)((a.B + kThreads - 1) / kThreads);
-  solve_fused_kernel<D, T, F, FIELD><<<grid, kThreads, 0, stream>>>(a);
+#ifdef TODE_FUSED_TUNE
+  // tuning build only: pick the occupancy variant at run time
+  const char* env = std::getenv("TODE_FUSED_MINB");
+  const int minb = env ? std::atoi(env) : TODE_FUSED_MINB;
+  switch (minb) {
+    case 3: solve_fused_kernel<D, T, F, FIELD, 3><<<grid, kThreads, 0, stream>>>(a); break;
+    case 5: solve_fused_kernel<D, T, F, FIELD, 5><<<grid, kThreads, 0, stream>>>(a); break;
+    case 6: solve_fused_kernel<D, T, F, FIELD, 6><<<grid, kThreads, 0, stream>>>(a); break;
+    case 8: solve_fused_kernel<D, T, F, FIELD, 8><<<grid, kThreads, 0, stream>>>(a); break;
+    default: solve_fused_kernel<D, T, F, FIELD, 4><<<grid, kThreads, 0, stream>>>(a); break;
+  }
+#else
+  solve_fused_kernel<D, T, F, FIELD, TODE_FUSED_MINB><<<grid, kThreads, 0, stream>>>(a);
+#endif
   return launch_status();
 }
 
