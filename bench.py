@@ -434,6 +434,7 @@ def main():
         # per-rank accepted steps of ONE step (every step solves the same inputs)
         local = solver.solve(problem)
         acc_local = int(local.stats["n_accepted"].sum())
+        attempted_local = int(local.stats["n_steps"].sum())
         iters = (int(local.stats["n_f_evals"][0]) - 2) // 6
         n_status = int((local.status != 0).sum())
         mean_steps = float(local.stats["n_steps"].float().mean())
@@ -504,7 +505,15 @@ def main():
     if not args.no_extras and world == 1:
         try:
             peak_fma = measure_fp64_peak(device)  # tera-FMA/s
-            line["fp64_issue"] = {"peak_tfma_per_s": peak_fma, "peak_source": "tode_bench_fp64_fma, measured live"}
+            # fp64-pipe instructions (DFMA+DMUL+DADD+DSETP) per attempted sample-step of the fused
+            # Tsit5+PID Van der Pol kernel, from the ncu opcode mix (profiles/r01_ncu_fused_c2.txt)
+            ops_per_step = 314
+            achieved = attempted_local / (kernel_ms * 1e-3) * ops_per_step / 1e12
+            line["fp64_issue"] = {
+                "peak_tfma_per_s": peak_fma, "peak_source": "tode_bench_fp64_fma, measured live",
+                "fp64_pipe_instr_per_attempted_step": ops_per_step,
+                "achieved_tinstr_per_s": achieved, "frac": achieved / peak_fma,
+                "note": "only meaningful for the fp64 workload (c2)"}
         except Exception as exc:  # measurement aid only
             line["fp64_issue"] = {"error": str(exc)}
         try:

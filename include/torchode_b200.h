@@ -258,6 +258,15 @@ int tode_interp_eval(const tode_tableau* tab, int32_t data_dtype, int32_t time_d
                      const void* y0, const void* y1, const void* const* k, const void* t,
                      const int64_t* idx, void* out, void* stream);
 
+/* Neural-ODE vector field on the tensor cores (BASELINE.json configs[3]): out = MLP(y) for a
+ * width-256 tanh MLP with n_layers linear layers (tanh between them, none after the last):
+ * bf16 operands, fp32 accumulation (tcgen05.mma into TMEM), fp32 bias, fp32 in/out.
+ * y, out: (B,256) float32 row-major; weights_bf16: (n_layers,256,256) bfloat16, [layer][out][in]
+ * (the layout of torch.nn.Linear.weight); biases_f32: (n_layers,256) float32.
+ * This is a user-level f (terms.py:60-63 calls it), not part of the solver arithmetic. */
+int tode_mlp_tanh256_forward(const void* y, const void* weights_bf16, const void* biases_f32,
+                             void* out, int64_t B, int32_t n_layers, void* stream);
+
 /* Measurement aid for bench.py (not on the solve path): every thread of a machine-filling
  * grid runs `iters` rounds of 8 independent double-precision FMA chains; writes one double
  * per thread to `sink` (at least tode_bench_fp64_fma_threads() doubles).  Returns the number

@@ -14,8 +14,11 @@ __global__ void summary_init_kernel(int* summary) {
   summary[3] = 0;
 }
 
+// resident 128-thread CTAs per SM the fused kernel is compiled for; measured on C2 / C3
+// (profiles/r01_fused_occupancy.txt): fp64 state prefers 6 (80 registers, a few spilled bytes,
+// -5 % time), fp32 state 4
 #ifndef TODE_FUSED_MINB
-#define TODE_FUSED_MINB 4
+#define TODE_FUSED_MINB (sizeof(D) == 8 ? 6 : 4)
 #endif
 
 template <typename D, typename T, int F, int FIELD>

@@ -77,3 +77,58 @@ class LotkaVolterra(BuiltinField):
         dx = self.alpha * x - self.beta * xz
         dz = self.delta * xz - self.gamma * z
         return torch.stack((dx, dz), dim=1)
+
+
+class TanhMLP256(nn.Module):
+    """Neural-ODE vector field ``y -> W_L tanh(... tanh(W_1 y + b_1) ...) + b_L`` of width 256
+    (BASELINE.json configs[3]) evaluated by ONE hand-written tcgen05 kernel per call: bf16 tensor
+    core GEMMs with fp32 accumulation in TMEM, bias + tanh epilogue out of TMEM, the activation
+    tile stays in shared memory between layers (``tode_mlp_tanh256_forward``).
+
+    It is an ordinary ``f`` for ``ODETerm`` (autonomous: ``t`` is ignored) and runs through the
+    stage-wise route.  ``forward_reference`` is the same computation in plain PyTorch fp32 ops
+    on the bf16-rounded operands (for tests and for running the field on the reference).
+    """
+
+    WIDTH = 256
+
+    def __init__(self, weights: torch.Tensor, biases: torch.Tensor):
+        super().__init__()
+        assert weights.ndim == 3 and weights.shape[1:] == (self.WIDTH, self.WIDTH)
+        assert biases.shape == (weights.shape[0], self.WIDTH)
+        self.register_buffer("weights", weights.detach().to(torch.bfloat16).contiguous())
+        self.register_buffer("biases", biases.detach().to(torch.float32).contiguous())
+
+    @staticmethod
+    def from_sequential(seq: nn.Sequential) -> "TanhMLP256":
+        linears = [m for m in seq if isinstance(m, nn.Linear)]
+        others = [m for m in seq if not isinstance(m, (nn.Linear, nn.Tanh))]
+        assert linears and not others, "expected Linear layers separated by Tanh"
+        return TanhMLP256(torch.stack([m.weight for m in linears]), torch.stack([m.bias for m in linears]))
+
+    @property
+    def n_layers(self) -> int:
+        return self.weights.shape[0]
+
+    def forward(self, t, y):
+        import ctypes as C
+
+        from . import _launch
+
+        _launch.require_cuda(y, self.weights)
+        assert y.dtype == torch.float32 and y.ndim == 2 and y.shape[1] == self.WIDTH
+        y = _launch.dense16(y)
+        out = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            _cabi.check(_cabi.lib().tode_mlp_tanh256_forward(
+                y.data_ptr(), self.weights.data_ptr(), self.biases.data_ptr(), out.data_ptr(), y.shape[0],
+                self.n_layers, _launch.stream_ptr(y.device)), "tode_mlp_tanh256_forward")
+        return out
+
+    def forward_reference(self, t, y):
+        h = y.to(torch.bfloat16).to(torch.float32)
+        for layer in range(self.n_layers):
+            h = h @ self.weights[layer].to(torch.float32).T + self.biases[layer]
+            if layer + 1 < self.n_layers:
+                h = torch.tanh(h).to(torch.bfloat16).to(torch.float32)
+        return h
