@@ -129,7 +129,107 @@ class C1(Workload):
         return batch * (4 + 8 + T * 8 + 32)
 
 
-WORKLOADS = {"c2": (C2, 1 << 20), "c3": (C3, 1 << 24), "c1": (C1, 2)}
+def _mlp_field(device=None):
+    """configs[3]: Sequential(Linear(256,256), Tanh, Linear, Tanh, Linear), default init under
+    torch.manual_seed(1234), weights x3 -> the tcgen05 field."""
+    from torchode_b200.fields import TanhMLP256
+
+    torch.manual_seed(1234)
+    seq = torch.nn.Sequential(torch.nn.Linear(256, 256), torch.nn.Tanh(), torch.nn.Linear(256, 256),
+                              torch.nn.Tanh(), torch.nn.Linear(256, 256))
+    with torch.no_grad():
+        for p in seq.parameters():
+            p.mul_(3.0)
+    f = TanhMLP256.from_sequential(seq)
+    return f if device is None else f.to(device)
+
+
+class C4(Workload):
+    """Neural ODE: 3x256 tanh MLP (tcgen05 bf16 field), Dopri5 + I(1e-6,1e-3), fp32 state, t in [0,10]."""
+
+    data_dtype, dtype_name = torch.float32, "f32"
+    staged, graph = True, True
+
+    def host_inputs(self, rank, batch):
+        g = torch.Generator().manual_seed(1234 + rank)
+        return dict(y0=torch.randn(batch, 256, generator=g), t_start=torch.zeros(batch),
+                    t_end=torch.full((batch,), 10.0), t_eval=None)
+
+    def components(self, device=None):
+        field = _mlp_field(device)
+        term = to.ODETerm(field)
+        return field, to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term)
+
+    def describe(self):
+        return ("configs[3]: neural ODE, 3x256 tanh MLP field on tcgen05 (bf16 GEMM, fp32 state), Dopri5+"
+                "I(1e-6,1e-3), t in [0,10], stage-wise route with CUDA-graph replay")
+
+    def algorithmic_bytes(self, batch, T):
+        return None
+
+    def numpy_field(self):
+        f = _mlp_field()
+        W = f.weights.float().numpy()
+        b = f.biases.numpy()
+
+        def bf16(x):
+            return torch.from_numpy(x).to(torch.bfloat16).float().numpy()
+
+        def fn(t, y):
+            h = bf16(y)
+            for l in range(3):
+                h = h @ W[l].T + b[l]
+                if l < 2:
+                    h = bf16(np.tanh(h))
+            return h.astype(np.float32)
+        return fn
+
+
+class C5(Workload):
+    """1-D heat equation, method of lines (opaque stencil f), Tsit5 + I(1e-6,1e-3), fp32, dim 2^20."""
+
+    data_dtype, dtype_name = torch.float32, "f32"
+    staged, graph = True, False
+    N = 1 << 20
+    KAPPA = 25.0
+
+    def host_inputs(self, rank, batch, n=None):
+        n = n or self.N
+        g = torch.Generator().manual_seed(1234 + rank)
+        x = torch.linspace(0, 1, n)
+        amp = torch.rand(batch, 3, generator=g)
+        y0 = sum(amp[:, k - 1:k] * torch.sin(k * torch.pi * x)[None] for k in (1, 2, 3))
+        return dict(y0=y0, t_start=torch.zeros(batch), t_end=torch.ones(batch), t_eval=None)
+
+    def components(self, device=None):
+        kappa = self.KAPPA
+
+        def field(t, y):
+            out = torch.zeros_like(y)
+            out[:, 1:-1] = kappa * ((y[:, 2:] - 2 * y[:, 1:-1]) + y[:, :-2])
+            return out
+
+        term = to.ODETerm(field)
+        return field, to.Tsit5(term), to.IntegralController(1e-6, 1e-3, term=term)
+
+    def describe(self):
+        return ("configs[4]: 1-D heat equation method of lines (PyTorch stencil f), Tsit5+I(1e-6,1e-3), "
+                "batch 64, dim 2^20, fp32, stage-wise route (split-mode finish)")
+
+    def algorithmic_bytes(self, batch, T):
+        return None
+
+    def numpy_field(self):
+        kappa = np.float32(self.KAPPA)
+
+        def fn(t, y):
+            out = np.zeros_like(y)
+            out[:, 1:-1] = kappa * ((y[:, 2:] - np.float32(2) * y[:, 1:-1]) + y[:, :-2])
+            return out
+        return fn
+
+
+WORKLOADS = {"c2": (C2, 1 << 20), "c3": (C3, 1 << 24), "c1": (C1, 2), "c4": (C4, 8192), "c5": (C5, 64)}
 
 
 def make_problem(host, device):
@@ -213,6 +313,8 @@ def cpu_run(workload, sample_batch, repeats=1):
     from oracle import oracle as orc
     from torchode_b200.single_step_methods import ExplicitRungeKutta  # noqa: F401
 
+    if getattr(workload, "staged", False):
+        return cpu_run_opaque(workload, sample_batch)
     field, method, ctrl = workload.components()
     host = workload.host_inputs(0, sample_batch)
     tab = method.to_cabi()
@@ -235,8 +337,27 @@ def cpu_run(workload, sample_batch, repeats=1):
     return acc / best, best, acc
 
 
+def cpu_run_opaque(workload, sample_batch):
+    """Opaque-f workloads: the oracle's C ops driven around a numpy restatement of f."""
+    from oracle import driver
+
+    _, method, ctrl = workload.components()
+    if workload.name == "c5":
+        host = workload.host_inputs(0, sample_batch, n=1 << 16)  # bounded: 2^16 of the 2^20 grid points
+    else:
+        host = workload.host_inputs(0, sample_batch)
+    tab = method.to_cabi()
+    cc = ctrl.to_cabi(method.convergence_order(), host["y0"].dtype)
+    t0 = time.perf_counter()
+    out = driver.solve_opaque(workload.numpy_field(), tab, cc, host["y0"].numpy(), host["t_start"].numpy(),
+                              host["t_end"].numpy())
+    dt = time.perf_counter() - t0
+    acc = int(out["n_accepted"].sum())
+    return acc / dt, dt, acc
+
+
 def cpu_sample_size(workload):
-    return {"c2": 1 << 17, "c3": 1 << 20, "c1": 2}[workload.name]
+    return {"c2": 1 << 17, "c3": 1 << 20, "c1": 2, "c4": 1024, "c5": 8}[workload.name]
 
 
 def cpu_cores():
@@ -364,7 +485,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))  # c2 = BASELINE configs[1]
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the config's)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / kernel rooflines")
@@ -396,8 +517,12 @@ def main():
     host_pinned = {k: (None if v is None else v.pin_memory()) for k, v in host.items()}
     problem = make_problem(host, device)
     T = problem.n_evaluation_points
-    field, method, ctrl = workload.components()
+    if getattr(workload, "staged", False):
+        field, method, ctrl = workload.components(device)
+    else:
+        field, method, ctrl = workload.components()
     solver = to.AutoDiffAdjoint(method, ctrl)
+    solver.use_cuda_graph = getattr(workload, "graph", False)
     l2buf = torch.zeros(128 << 20, dtype=torch.float32, device=device)  # 512 MiB
 
     def step():
@@ -436,6 +561,7 @@ def main():
         acc_local = int(local.stats["n_accepted"].sum())
         attempted_local = int(local.stats["n_steps"].sum())
         iters = (int(local.stats["n_f_evals"][0]) - 2) // 6
+        last_run = dict(solver.last_run)
         n_status = int((local.status != 0).sum())
         mean_steps = float(local.stats["n_steps"].float().mean())
 
@@ -476,8 +602,15 @@ def main():
     # ---- roofline of the dominant kernel (the fused whole-solve kernel) -----------------------
     kernel_ms = statistics.median(times) if world == 1 else ms_per_step
     alg_bytes = workload.algorithmic_bytes(B, T)
+    if alg_bytes is None:
+        # stage-wise workloads: solver-owned algorithmic traffic = 44 F e per attempted sample-step
+        # (DESIGN.md section 4); the user's f is not part of it
+        e = 4 if workload.dtype_name == "f32" else 8
+        alg_bytes = 44 * int(problem.n_features) * e * attempted_local
     roofline = {
-        "kernel": "solve_fused_kernel", "bound": "hbm", "achieved": alg_bytes / kernel_ms / 1e6,
+        "kernel": "solve_fused_kernel" if last_run.get("route", "").startswith("fused") else
+                  "erk_stage_kernel x6 + erk_finish_kernel (whole staged step incl. the user's f)",
+        "bound": "hbm", "achieved": alg_bytes / kernel_ms / 1e6,
         "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / kernel_ms / 1e6 / hbm_peak, "traffic": None,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
         "note": ("whole solve in registers: HBM is touched only for inputs/outputs; for C2 the kernel is "
@@ -497,7 +630,9 @@ def main():
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(e2e_s) * 1e3},
-        "gpu_launches": 2 * args.steps,  # summary_init_kernel + solve_fused_kernel per step
+        # fused: summary_init_kernel + solve_fused_kernel per step; staged: init + 7 per iteration
+        "gpu_launches": int(last_run.get("kernel_launches", last_run.get("kernel_launches_min", 0))) * args.steps,
+        "route": last_run,
         "wall_s_timed_region": t_wall,
     }
     if clocks is not None:

@@ -24,7 +24,7 @@ if __name__ == "__main__":
         cls, batch = bench.WORKLOADS[which]
         w = cls(which, batch)
         prob = bench.make_problem(w.host_inputs(0, w.batch), dev)
-        _, method, ctrl = w.components()
+        _, method, ctrl = w.components(dev) if getattr(w, "staged", False) else w.components()
         solver = bench.to.AutoDiffAdjoint(method, ctrl)
         with torch.no_grad():
             for _ in range(2):

@@ -49,6 +49,8 @@ class AutoDiffAdjoint(nn.Module):
         #: capturable (no host sync, no data-dependent Python control flow) and free of host side
         #: effects.  Removes the launch latency that dominates small problems.
         self.use_cuda_graph = False
+        #: bookkeeping of the last solve: route taken and number of kernels launched through the C-ABI
+        self.last_run = {}
 
     # ------------------------------------------------------------------------------------
     def _kernel_route(self) -> bool:
@@ -129,10 +131,12 @@ class AutoDiffAdjoint(nn.Module):
         iters, first_fail, nonmono, _ = run(0)
         if nonmono:
             return None  # t_eval rows not monotone in time: the staged route has the general mode
+        self.last_run = {"route": "fused", "kernel_launches": 2, "iterations": iters}
         if first_fail != _INT32_MAX and first_fail < iters:
             # a failure stops the WHOLE batch at that iteration (adjoints.py:186-190): replay
             # with every sample limited to the iterations the reference would have executed
             iters, _, _, _ = run(first_fail)
+            self.last_run = {"route": "fused+replay", "kernel_launches": 4, "iterations": iters}
         stats: Dict[str, Any] = {}
         term_.init(problem, stats)
         if "n_f_evals" in stats:
@@ -233,6 +237,10 @@ class AutoDiffAdjoint(nn.Module):
         torch.cuda.current_stream(dev).synchronize()
         ctl_host = st.ctl.tolist()
         iters = ctl_host[_cabi.CTL_ITERS]
+        self.last_run = {"route": "staged+graph" if graph is not None else "staged", "iterations": iters,
+                         "iterations_launched": launched,
+                         # 6 stage kernels + finish (3 launches in split mode) per launched iteration, + init
+                         "kernel_launches_min": launched * S + (2 if dt0 is None else 1)}
         if "n_f_evals" in stats:
             # speculative iterations after the stop flag are no-ops on the device
             stats["n_f_evals"].fill_(n_init_evals + (S - 1) * iters)
