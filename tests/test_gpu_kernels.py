@@ -404,3 +404,26 @@ def test_tsit5_dense_output_recovers_a_quartic():
     want = (t_eval**4 - t_eval**2 + c[:, None])[:, :, None]
     assert (sol.stats["n_initialized"] == 31).all()
     assert torch.allclose(sol.ys, want, atol=5e-4)
+
+
+def test_cuda_graph_plan_is_reused_across_solves_with_new_inputs():
+    B = 300
+    field = to.fields.LotkaVolterra()
+    term = to.ODETerm(lambda t, y: field(t, y))
+    graph_solver = to.AutoDiffAdjoint(to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term))
+    graph_solver.use_cuda_graph = True
+    plain_solver = to.AutoDiffAdjoint(to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term))
+    t_eval = torch.linspace(0, 4, 12, device=DEV).expand(B, 12)
+    previous = None
+    for seed in range(3):
+        g = torch.Generator().manual_seed(seed)
+        y0 = (1 + torch.rand(B, 2, generator=g)).to(DEV)
+        with torch.no_grad():
+            a = graph_solver.solve(to.InitialValueProblem(y0, t_eval=t_eval))
+            b = plain_solver.solve(to.InitialValueProblem(y0, t_eval=t_eval))
+        assert torch.equal(a.ys, b.ys) and torch.equal(a.stats["n_steps"], b.stats["n_steps"])
+        assert a.stats["n_f_evals"].tolist() == b.stats["n_f_evals"].tolist()
+        if previous is not None:  # earlier solutions are not clobbered by the reused buffers
+            assert torch.equal(previous[0].ys, previous[1])
+        previous = (a, a.ys.clone())
+    assert len(graph_solver._plans) == 1 and graph_solver.last_run["route"] == "staged+graph"

@@ -150,20 +150,31 @@ def adapt_step_size(controller, state, dt, y0, y1, err):
 class StagedState:
     """Device buffers of one stage-wise ("path A") solve and the ``tode_state`` over them."""
 
-    def __init__(self, problem, n_stages: int, pid: bool, general: bool = False):
+    def __init__(self, problem, n_stages: int, pid: bool, general: bool = False, persistent: bool = False):
+        """``persistent``: own copies of the problem tensors, so that the same buffers (and a CUDA
+        graph recorded over them) can be reused for later problems of the same shape (`rebind`)."""
         y0 = dense16(problem.y0)
         dev, D, Tt = y0.device, y0.dtype, problem.time_dtype
         B, F = y0.shape
         Tn = problem.n_evaluation_points
         self.B, self.F, self.T, self.device = B, F, Tn, dev
+        self.persistent = persistent
         self.t_start, self.t_end = problem.t_start.contiguous(), problem.t_end.contiguous()
+        if persistent:
+            self.t_start, self.t_end = self.t_start.clone(), self.t_end.clone()
         self.t_eval, stride_b = None, 0
+        self.t_eval_broadcast = False
         if problem.t_eval is not None:
             te = problem.t_eval
             if te.stride(0) == 0 and (Tn <= 1 or te.stride(1) == 1):
                 self.t_eval = te  # broadcast row (e.g. solve_ivp's expand): no 6.4 GB copy
+                self.t_eval_broadcast = True
+                if persistent:
+                    self.t_eval = te[0].clone()
             else:
                 self.t_eval, stride_b = te.contiguous(), Tn
+                if persistent and self.t_eval.data_ptr() == te.data_ptr():
+                    self.t_eval = self.t_eval.clone()
         self.t = torch.empty(B, dtype=Tt, device=dev)
         self.dt = torch.empty(B, dtype=Tt, device=dev)
         self.y = y0.clone()
@@ -196,6 +207,17 @@ class StagedState:
         st.y_eval, st.t_nodes, st.ctl = self.y_eval.data_ptr(), self.t_nodes.data_ptr(), self.ctl.data_ptr()
         st.scratch, st.scratch_elems = self.scratch.data_ptr(), n_scr
         self.c = st
+
+    def rebind(self, problem):
+        """Load another problem of the same shape / layout into the persistent buffers."""
+        assert self.persistent
+        self.y.copy_(problem.y0)
+        self.t_start.copy_(problem.t_start)
+        self.t_end.copy_(problem.t_end)
+        if self.t_eval is not None:
+            self.t_eval.copy_(problem.t_eval[0] if self.t_eval_broadcast else problem.t_eval)
+        if self.not_yet is not None:
+            self.not_yet.fill_(1)
 
 
 def select_initial_step(controller, term, problem, method_order, stats, args):

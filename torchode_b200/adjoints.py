@@ -51,6 +51,21 @@ class AutoDiffAdjoint(nn.Module):
         self.use_cuda_graph = False
         #: bookkeeping of the last solve: route taken and number of kernels launched through the C-ABI
         self.last_run = {}
+        # staged route with use_cuda_graph: persistent buffers + recorded iteration graph per
+        # problem signature, reused by later solves (capture + instantiation cost ~10-50 ms)
+        self._plans = {}
+        self._rings = {}
+
+    def _poll_ring(self, dev, look):
+        """Pinned host mirror of the control block + events, allocated once per solver and device
+        (cudaHostAlloc costs far more than a loop iteration)."""
+        key = (str(dev), look)
+        ring = self._rings.get(key)
+        if ring is None:
+            ring = (torch.zeros((look + 1, _cabi.CTL_WORDS), dtype=torch.int32).pin_memory(),
+                    [torch.cuda.Event() for _ in range(look + 1)])
+            self._rings[key] = ring
+        return ring
 
     # ------------------------------------------------------------------------------------
     def _kernel_route(self) -> bool:
@@ -157,7 +172,23 @@ class AutoDiffAdjoint(nn.Module):
         cab_t = method.to_cabi()
         cab_c = ctrl.to_cabi(method.convergence_order(), D, self.max_steps)
         S = cab_t.n_stages
-        st = _launch.StagedState(problem, S, bool(cab_c.pid), general=general)
+        plan = None
+        if self.use_cuda_graph:
+            te = problem.t_eval
+            key = (str(dev), B, F, Tn, D, Tt, general, id(term_.f), id(args), dt0 is None,
+                   None if te is None else (te.stride(0) == 0), bytes(cab_t), bytes(cab_c))
+            plan = self._plans.get(key)
+            if plan is None:
+                if len(self._plans) >= 4:
+                    self._plans.clear()
+                plan = {"st": _launch.StagedState(problem, S, bool(cab_c.pid), general=general, persistent=True),
+                        "graph": None, "kp": None, "ks": None}
+                self._plans[key] = plan
+            else:
+                plan["st"].rebind(problem)
+            st = plan["st"]
+        else:
+            st = _launch.StagedState(problem, S, bool(cab_c.pid), general=general)
         stream = _launch.stream_ptr(dev)
         tab_p, ctrl_p, st_p = C.byref(cab_t), C.byref(cab_c), C.byref(st.c)
         stats: Dict[str, Any] = {}
@@ -190,11 +221,13 @@ class AutoDiffAdjoint(nn.Module):
 
         # ---- the loop: never blocks on the iteration just launched ---------------------------
         look = max(1, int(self.lookahead))
-        pinned = torch.zeros((look + 1, _cabi.CTL_WORDS), dtype=torch.int32).pin_memory()
-        events = [torch.cuda.Event() for _ in range(look + 1)]
-        kp = _cabi.KPtrs()
-        kp[0] = st.f0.data_ptr()
-        ks = [st.f0] + [None] * (S - 1)
+        pinned, events = self._poll_ring(dev, look)
+        if plan is not None and plan["kp"] is not None:
+            kp, ks = plan["kp"], plan["ks"]
+        else:
+            kp = _cabi.KPtrs()
+            kp[0] = st.f0.data_ptr()
+            ks = [st.f0] + [None] * (S - 1)
         stage, finish = lib.tode_erk_stage, lib.tode_erk_finish
         y_stage, t_nodes = st.y_stage, st.t_nodes
 
@@ -213,14 +246,15 @@ class AutoDiffAdjoint(nn.Module):
 
         launched = 0
         ctl_host = None
-        graph = None
+        graph = plan["graph"] if plan is not None else None
         while True:
             if graph is not None:
                 graph.replay()
             else:
                 launch_iteration(stream)
-                if self.use_cuda_graph and launched == 0:
+                if plan is not None and launched == 0:
                     graph = self._capture_iteration(launch_iteration, dev)
+                    plan["graph"], plan["kp"], plan["ks"] = graph, kp, ks
             slot = launched % (look + 1)
             pinned[slot].copy_(st.ctl, non_blocking=True)
             events[slot].record()
@@ -257,7 +291,9 @@ class AutoDiffAdjoint(nn.Module):
         else:
             stats["n_initialized"] = torch.ones(B, dtype=torch.long, device=dev)
             ts = problem.t_end[:, None]
-        return Solution(ts=ts, ys=st.y_eval, stats=stats, status=st.status.to(torch.long))
+        # persistent (graph-cached) buffers are overwritten by the next solve: hand out a copy
+        ys = st.y_eval.clone() if st.persistent else st.y_eval
+        return Solution(ts=ts, ys=ys, stats=stats, status=st.status.to(torch.long))
 
     @staticmethod
     def _capture_iteration(launch_iteration, dev):

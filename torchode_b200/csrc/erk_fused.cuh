@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
     }
 
     D r1 = (D)1, r2 = (D)1;
+    double L1 = 0.0, L2 = 0.0;  // log2 of the PID history, carried instead of recomputed (same bits)
     bool running = true;
     // ---- the loop (adjoints.py:135-260) ---------------------------------------------------
     while (running && status == TODE_SUCCESS && (A.iter_cap <= 0 || ns < A.iter_cap)) {
@@ -220,7 +221,8 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
         for (int f = 0; f < F; ++f) v[f] = fdiv(q[f], sqrt_f);
         nrm = fsqrt(row_sumsq_canonical<D, F>(v));
       }
-      const CtrlOut<D, T> o = controller<D, T>(c, nrm, dt, r1, r2);
+      double Lr;
+      const CtrlOut<D, T> o = controller_l<D, T>(c, nrm, dt, r1, r2, L1, L2, &Lr);
       const bool upd = o.accept;                 // running is true inside the loop
       const T t_new = upd ? add(t, dt) : t;      // adjoints.py:151
       ns += 1;                                   // :161
@@ -275,6 +277,10 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
       T dt_new = running_new ? o.dt_next : dt;                          // :247
       dt = clamp_nan(dt_new, sub(t_min, t_new), sub(t_max, t_new));     // :251
       if (c.pid && running_new) {                                       // :253-255
+        if (o.accept) {
+          L2 = L1;
+          L1 = Lr;
+        }
         r1 = o.r1;
         r2 = o.r2;
       }
