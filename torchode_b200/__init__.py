@@ -10,6 +10,7 @@ __version__ = "0.1.0"
 
 from . import fields
 from .adjoints import AutoDiffAdjoint
+from .backsolve import BacksolveAdjoint, JointBacksolveAdjoint
 from .interface import register_method, solve_ivp
 from .problems import InitialValueProblem
 from .single_step_methods import Dopri5, Tsit5

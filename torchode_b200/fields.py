@@ -53,9 +53,9 @@ class VanDerPol(BuiltinField):
         return [self.mu]
 
     def forward(self, t, y):
-        x, v = y[:, 0], y[:, 1]
+        x, v = y[..., 0], y[..., 1]  # `...`: also valid for an unbatched sample (torch.func.vmap)
         dv = self.mu * (1 - x * x) * v - x
-        return torch.stack((v, dv), dim=1)
+        return torch.stack((v, dv), dim=-1)
 
 
 class LotkaVolterra(BuiltinField):
@@ -72,11 +72,11 @@ class LotkaVolterra(BuiltinField):
         return [self.alpha, self.beta, self.delta, self.gamma]
 
     def forward(self, t, y):
-        x, z = y[:, 0], y[:, 1]
+        x, z = y[..., 0], y[..., 1]
         xz = x * z
         dx = self.alpha * x - self.beta * xz
         dz = self.delta * xz - self.gamma * z
-        return torch.stack((dx, dz), dim=1)
+        return torch.stack((dx, dz), dim=-1)
 
 
 class TanhMLP256(nn.Module):
