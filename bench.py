@@ -367,7 +367,7 @@ def cpu_cores():
         return os.cpu_count() or 1
 
 
-def run_reference_arm(args, workload):
+def run_reference_arm(args, workload, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -390,7 +390,7 @@ def run_reference_arm(args, workload):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    out.emit(json.dumps(line))
     return 0
 
 
@@ -480,7 +480,33 @@ def measure_fp64_peak(device):
 
 
 # --------------------------------------------------------------------------------------------
+class _StdoutGuard:
+    """Exactly ONE JSON line on stdout: everything else (NCCL banners, library chatter) that would
+    be written to fd 1 during the run goes to stderr."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def main():
+    with _StdoutGuard() as out:
+        return _main(out)
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -495,7 +521,7 @@ def main():
     cls, batch = WORKLOADS[args.workload]
     workload = cls(args.workload, args.batch or batch)
     if args.impl == "reference":
-        return run_reference_arm(args, workload)
+        return run_reference_arm(args, workload, out)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -664,7 +690,7 @@ def main():
                           f"{t:.1f} s"}
         except Exception as exc:
             line["cpu_baseline"] = {"error": str(exc)}
-    print(json.dumps(line))
+    out.emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -54,21 +54,22 @@ def _gather_rows(x: torch.Tensor, sizes, group) -> torch.Tensor:
 
 def gather_solution(local: Solution, global_batch: int, ts: Optional[torch.Tensor] = None,
                     group=None) -> Solution:
-    """Assemble the full-batch Solution on every rank from the per-rank ones."""
+    """Assemble the full-batch Solution on every rank from the per-rank ones: one all_gather for
+    ``ys``, one for the stacked int64 statistics, one all_reduce(MAX) for the iteration count."""
     world = dist.get_world_size(group)
     sizes = [hi - lo for lo, hi in (shard_bounds(global_batch, r, world) for r in range(world))]
     ys = _gather_rows(local.ys, sizes, group)
-    status = _gather_rows(local.status, sizes, group)
-    stats = {}
-    for key in ("n_steps", "n_accepted", "n_initialized"):
-        if key in local.stats:
-            stats[key] = _gather_rows(local.stats[key], sizes, group)
+    keys = [k for k in ("n_steps", "n_accepted", "n_initialized") if k in local.stats]
+    packed = torch.stack([local.status.to(torch.long)] + [local.stats[k].to(torch.long) for k in keys], dim=1)
+    packed = _gather_rows(packed, sizes, group)
+    status = packed[:, 0].contiguous()
+    stats = {k: packed[:, i + 1].contiguous() for i, k in enumerate(keys)}
     if "n_f_evals" in local.stats:
         # batch-uniform in the reference: every sample is charged the evaluations of the
         # longest-running one -> MAX over ranks
         n = local.stats["n_f_evals"][:1].to(ys.device, copy=True)
         dist.all_reduce(n, op=dist.ReduceOp.MAX, group=group)
-        stats["n_f_evals"] = n.cpu().expand(global_batch).clone()
+        stats["n_f_evals"] = torch.full((global_batch,), int(n.item()), dtype=torch.long)
     if ts is None:
         ts = _gather_rows(local.ts, sizes, group)
     return Solution(ts=ts, ys=ys, stats=stats, status=status)
