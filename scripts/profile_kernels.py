@@ -21,7 +21,11 @@ if __name__ == "__main__":
                 print(f"{r['kernel']:55s} {r['ms']:8.4f} ms {r['achieved']:8.1f} GB/s frac {r['frac']:.3f}"
                       + (f" acc {r['accepted_fraction']:.2f}" if 'accepted_fraction' in r else ""))
     else:
+        small = which.endswith("small")
+        which = which.replace("small", "")
         cls, batch = bench.WORKLOADS[which]
+        if small:
+            batch = 1 << 20
         w = cls(which, batch)
         prob = bench.make_problem(w.host_inputs(0, w.batch), dev)
         _, method, ctrl = w.components(dev) if getattr(w, "staged", False) else w.components()

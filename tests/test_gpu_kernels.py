@@ -427,3 +427,82 @@ def test_cuda_graph_plan_is_reused_across_solves_with_new_inputs():
             assert torch.equal(previous[0].ys, previous[1])
         previous = (a, a.ys.clone())
     assert len(graph_solver._plans) == 1 and graph_solver.last_run["route"] == "staged+graph"
+
+
+@pytest.mark.parametrize("method_cls", [to.Heun, to.Euler, to.Dopri5, to.Tsit5])
+def test_fixed_step_methods_follow_the_analytic_solution(method_cls):
+    """fixed_step_controller_test.py:10-19 incl. Heun; Euler gets a finer step."""
+    B = 3
+    y0 = torch.full((B, 2), 2.0, device=DEV, dtype=torch.float64)
+    t_eval = torch.linspace(0, 1.5, 7, device=DEV, dtype=torch.float64).repeat(B, 1)
+    term = to.ODETerm(lambda t, y: -y)
+    solver = to.AutoDiffAdjoint(method_cls(term), to.FixedStepController())
+    dt = 0.002 if method_cls is to.Euler else 0.05
+    with torch.no_grad():
+        sol = solver.solve(to.InitialValueProblem(y0, t_eval=t_eval),
+                           dt0=torch.full((B,), dt, device=DEV, dtype=torch.float64))
+    assert (sol.status == 0).all() and (sol.stats["n_initialized"] == 7).all()
+    assert torch.allclose(sol.ys[:, :, 0], 2.0 * torch.exp(-t_eval), rtol=1e-2)
+
+
+@pytest.mark.parametrize("time_dtype,data_dtype", [(torch.float32, torch.float64), (torch.float64, torch.float32)])
+@pytest.mark.parametrize("method_cls", [to.Heun, to.Dopri5, to.Tsit5])
+def test_time_and_data_dtypes_never_mix(method_cls, time_dtype, data_dtype):
+    """dtype_stability_test.py:15-42: adaptive Heun / Dopri5 / Tsit5 + PID with different dtypes."""
+    B = 4
+    y0 = torch.ones(B, 3, device=DEV, dtype=data_dtype)
+    t_eval = torch.linspace(0, 1, 5, device=DEV, dtype=time_dtype).repeat(B, 1)
+
+    def f(t, y):
+        assert t.dtype == time_dtype and y.dtype == data_dtype
+        return -y * t[:, None].to(data_dtype)
+
+    term = to.ODETerm(f)
+    solver = to.AutoDiffAdjoint(method_cls(term), to.PIDController(1e-5, 1e-5, 0.2, 0.5, 0.0, term=term))
+    with torch.no_grad():
+        sol = solver.solve(to.InitialValueProblem(y0, t_eval=t_eval))
+    assert sol.ys.dtype == data_dtype and sol.ts.dtype == time_dtype and (sol.status == 0).all()
+    want = torch.exp(-0.5 * t_eval.to(data_dtype) ** 2)[:, :, None].expand(-1, -1, 3)
+    assert torch.allclose(sol.ys, want, rtol=2e-3)
+
+
+def test_solve_ivp_with_registered_method_names():
+    y0 = torch.ones(2, 1, device=DEV, dtype=torch.float64)
+    t_eval = torch.linspace(0, 1, 4, device=DEV, dtype=torch.float64)
+    for name in ("heun", "dopri5", "tsit5"):
+        with torch.no_grad():
+            sol = to.solve_ivp(lambda t, y: -y, y0, t_eval, method=name)
+        assert torch.allclose(sol.ys[:, :, 0], torch.exp(-t_eval).expand(2, -1), rtol=1e-4), name
+
+
+def _lv_solver(staged):
+    field = to.fields.LotkaVolterra()
+    term = to.ODETerm((lambda t, y: field(t, y)) if staged else field)
+    return to.AutoDiffAdjoint(to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term))
+
+
+@pytest.mark.parametrize("staged", [False, True])
+def test_edge_cases_empty_batch_zero_span_and_strided_inputs(staged):
+    solver = _lv_solver(staged)
+    with torch.no_grad():
+        # empty batch
+        sol = solver.solve(to.InitialValueProblem(torch.empty(0, 2, device=DEV), torch.empty(0, device=DEV),
+                                                  torch.empty(0, device=DEV)))
+        assert sol.ys.shape == (0, 1, 2) and sol.stats["n_steps"].shape == (0,)
+        # t_start == t_end: one masked step with dt = 0 (time_direction = -1, SURVEY A.6)
+        y0 = torch.tensor([[1.0, 2.0], [1.5, 0.5]], device=DEV)
+        t = torch.tensor([0.0, 1.0], device=DEV)
+        sol = solver.solve(to.InitialValueProblem(y0, t, t.clone()))
+        assert sol.stats["n_steps"].tolist() == [1, 1] and sol.stats["n_accepted"].tolist() == [1, 1]
+        assert torch.equal(sol.ys[:, 0], y0) and (sol.status == 0).all()
+        # non-contiguous y0 / t_eval views, a single sample, an expanded scalar time
+        big = (1 + torch.rand(2, 7, device=DEV))
+        y0_view = big.T[:5]                       # (5, 2) with strides (1, 7)
+        te_big = torch.linspace(0, 2, 12, device=DEV).repeat(5, 1)
+        te_view = te_big[:, ::2]                  # every other column
+        a = solver.solve(to.InitialValueProblem(y0_view, t_eval=te_view))
+        b = solver.solve(to.InitialValueProblem(y0_view.contiguous(), t_eval=te_view.contiguous()))
+        assert torch.equal(a.ys, b.ys) and torch.equal(a.stats["n_steps"], b.stats["n_steps"])
+        one = solver.solve(to.InitialValueProblem(y0_view[:1], torch.zeros(1, device=DEV),
+                                                  torch.tensor(2.0, device=DEV).expand(1)))
+        assert one.ys.shape == (1, 1, 2) and (one.status == 0).all() and torch.isfinite(one.ys).all()

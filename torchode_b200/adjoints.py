@@ -90,6 +90,8 @@ class AutoDiffAdjoint(nn.Module):
             raise NotImplementedError(
                 "the CUDA solve loop is forward-only: wrap the call in torch.no_grad() (autograd "
                 "through the fused kernels is not implemented yet)")
+        if problem.batch_size == 0:
+            return self._empty_solution(problem, term_)
         with torch.no_grad(), torch.cuda.device(problem.device):
             f = term_.f
             if (isinstance(f, BuiltinField) and not term_.with_args and problem.n_features <= 4
@@ -98,6 +100,18 @@ class AutoDiffAdjoint(nn.Module):
                 if sol is not None:
                     return sol
             return self._solve_staged(problem, term_, dt0, args)
+
+    @staticmethod
+    def _empty_solution(problem, term_) -> Solution:
+        """Empty batch: nothing to launch (empty tensors have no device pointer to hand over)."""
+        dev, Tn = problem.device, problem.n_evaluation_points
+        stats: Dict[str, Any] = {}
+        term_.init(problem, stats)
+        zeros = torch.zeros(0, dtype=torch.long, device=dev)
+        stats["n_steps"], stats["n_accepted"], stats["n_initialized"] = zeros, zeros.clone(), zeros.clone()
+        ys = problem.y0.new_empty((0, max(Tn, 1), problem.n_features))
+        ts = problem.t_eval if problem.t_eval is not None else problem.t_end[:, None]
+        return Solution(ts=ts, ys=ys, stats=stats, status=zeros.clone())
 
     # ------------------------------------------------------------------------------------
     # route 1: fused whole-solve kernel

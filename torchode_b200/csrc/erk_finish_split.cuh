@@ -72,10 +72,10 @@ __global__ void __launch_bounds__(kBlock) finish_split_partial_kernel(const __gr
 #pragma unroll
           for (int s = 0; s < S; ++s) ks[s] = kv[s][x];
           const D err = weighted_sum<D, S>(dtD, tab.b_err, ks);
-          const D bounds = ffma(c.rtol, max_nan(fabs_(y0v[x]), fabs_(y1v[x])), c.atol);
+          const D bounds = ffma(c.rtol, max_nan_nn(fabs_(y0v[x]), fabs_(y1v[x])), c.atol);
           const D q = fdiv(fabs_(err), bounds);
           if (c.norm == TODE_NORM_MAX) {
-            part = first ? q : max_nan(part, q);
+            part = first ? fabs_(q) : max_nan_nn(part, fabs_(q));
             first = false;
           } else {
             sumsq_acc(part, first, fdiv(q, A.sqrt_f));
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kBlock) finish_split_control_kernel(const __gr
       D nrm;
       if (c.norm == TODE_NORM_MAX) {
         nrm = p[0];
-        for (long long ch = 1; ch < cpr; ++ch) nrm = max_nan(nrm, p[ch]);
+        for (long long ch = 1; ch < cpr; ++ch) nrm = max_nan_nn(nrm, p[ch]);
       } else {
         D total = p[0];
         for (long long ch = 1; ch < cpr; ++ch) total = add(total, p[ch]);  // ascending chunk order

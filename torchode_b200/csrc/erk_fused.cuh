@@ -157,10 +157,10 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
       for (int i = 0; i < F; ++i) q[i] = mul(sub(f1[i], k[0][i]), inv[i]);
       D d2 = fdiv(row_norm_small<D, F>(q, c.norm), dt0);
       if (!c.pid && dt0 == (D)0) d2 = (D)__longlong_as_double(0x7ff0000000000000LL);
-      const D m = max_nan(d1, d2);
+      const D m = max_nan_nn(d1, d2);
       D dt1;
       if (m <= (D)1e-15) {
-        dt1 = max_nan((D)1e-6, mul(dt0, (D)1e-3));
+        dt1 = max_nan_nn((D)1e-6, mul(dt0, (D)1e-3));
       } else {
         dt1 = det_pow_t(mul(fdiv((D)1, m), (D)0.01), A.e_init);
       }
@@ -207,14 +207,14 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
 #pragma unroll
         for (int s = 0; s < S; ++s) ks[s] = k[s][f];
         const D err = weighted_sum<D, S>(dtD, tab.b_err, ks);
-        const D bounds = ffma(c.rtol, max_nan(fabs_(y[f]), fabs_(y1[f])), c.atol);
+        const D bounds = ffma(c.rtol, max_nan_nn(fabs_(y[f]), fabs_(y1[f])), c.atol);
         q[f] = fdiv(fabs_(err), bounds);
       }
       D nrm;
       if (c.norm == TODE_NORM_MAX) {
-        nrm = q[0];
+        nrm = fabs_(q[0]);
 #pragma unroll
-        for (int f = 1; f < F; ++f) nrm = max_nan(nrm, q[f]);
+        for (int f = 1; f < F; ++f) nrm = max_nan_nn(nrm, fabs_(q[f]));
       } else {
         D v[F];
 #pragma unroll

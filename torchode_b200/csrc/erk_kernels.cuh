@@ -195,7 +195,7 @@ TODE_DEV D group_sum(D v) {
 template <typename D, int G>
 TODE_DEV D group_max(D v) {
 #pragma unroll
-  for (int m = 1; m < G; m <<= 1) v = max_nan(v, __shfl_xor_sync(0xffffffffu, v, m));
+  for (int m = 1; m < G; m <<= 1) v = max_nan_nn(v, __shfl_xor_sync(0xffffffffu, v, m));  // v >= 0 or NaN
   return v;
 }
 
@@ -216,7 +216,7 @@ struct RowNorm {
       : part((D)0), total((D)0), sqrt_f(sqrt_f_), cnt(0), kind(kind_), first(true), first_chunk(true) {}
   TODE_DEV void add(D q) {
     if (kind == TODE_NORM_MAX) {
-      part = first ? fabs_(q) : max_nan(part, fabs_(q));
+      part = first ? fabs_(q) : max_nan_nn(part, fabs_(q));
       first = false;
     } else {
       sumsq_acc(part, first, fdiv(q, sqrt_f));
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kBlock, finish_min_blocks<D, G, VEC>()) erk_fi
 #pragma unroll
         for (int s = 0; s < S; ++s) ks[s] = kv[s][x];
         const D err = weighted_sum<D, S>(dtD, tab.b_err, ks);  // runge_kutta.py:269
-        const D bounds = ffma(c.rtol, max_nan(fabs_(y0v[x]), fabs_(y1v[x])), c.atol);
+        const D bounds = ffma(c.rtol, max_nan_nn(fabs_(y0v[x]), fabs_(y1v[x])), c.atol);
         rn.add(fdiv(fabs_(err), bounds));
       }
     };
@@ -657,10 +657,10 @@ __global__ void __launch_bounds__(kBlock) init_step_b_kernel(const __grid_consta
       D d2 = fdiv(nrm2, dt0);
       // only the Integral copy guards dt0 == 0 (:481 vs :826)
       if (!c.pid && dt0 == (D)0) d2 = (D)__longlong_as_double(0x7ff0000000000000LL);
-      const D m = max_nan(d1, d2);
+      const D m = max_nan_nn(d1, d2);
       D dt1;
       if (m <= (D)1e-15) {
-        dt1 = max_nan((D)1e-6, mul(dt0, (D)1e-3));
+        dt1 = max_nan_nn((D)1e-6, mul(dt0, (D)1e-3));
       } else {
         // `0.01 / m` is Tensor.__rtruediv__ = m.reciprocal() * 0.01      (:484-488)
         dt1 = det_pow_t(mul(fdiv((D)1, m), (D)0.01), A.e_init);

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kBlock) adapt_kernel(const __grid_constant__ A
         VecIO<D, VEC>::ld(A.err + row + j * VEC, ev);
 #pragma unroll
         for (int x = 0; x < VEC; ++x) {
-          const D bounds = ffma(c.rtol, max_nan(fabs_(y0v[x]), fabs_(y1v[x])), c.atol);
+          const D bounds = ffma(c.rtol, max_nan_nn(fabs_(y0v[x]), fabs_(y1v[x])), c.atol);
           rn.add(fdiv(fabs_(ev[x]), bounds));
         }
       }

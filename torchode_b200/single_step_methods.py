@@ -12,9 +12,10 @@ import torch
 import torch.nn as nn
 
 from . import _cabi, _launch
-from .interpolation import FourthOrderPolynomialInterpolation, LocalInterpolation
+from .interpolation import (FourthOrderPolynomialInterpolation, LinearInterpolation, LocalInterpolation,
+                            ThirdOrderPolynomialInterpolation)
 from .problems import InitialValueProblem
-from .tableaus import DOPRI5, TSIT5, ButcherTableau
+from .tableaus import DOPRI5, EULER, HEUN, TSIT5, ButcherTableau
 from .terms import ODETerm
 
 
@@ -170,3 +171,55 @@ class Tsit5(ExplicitRungeKutta):
 
     def build_interpolation(self, data: ERKInterpolationData):
         return _KernelQuartic(self.to_cabi(), data)
+
+
+class Heun(ExplicitRungeKutta):
+    """Heun's 2nd-order method with cubic Hermite dense output (single_step_methods/heun.py).
+    Runs through the generic plug-in route: its stage combination, solution and error estimate
+    are the same CUDA ops (``tode_erk_stage`` / ``tode_erk_weighted_sum``)."""
+
+    TABLEAU = HEUN
+
+    def __init__(self, term: Optional[ODETerm] = None):
+        super().__init__(term, Heun.TABLEAU)
+
+    def convergence_order(self):
+        return 2
+
+    def build_interpolation(self, data: ERKInterpolationData):
+        return ThirdOrderPolynomialInterpolation.from_k(data.t0, data.dt, data.y0, data.y1, data.k)
+
+
+class LinearInterpolationData(NamedTuple):
+    t0: torch.Tensor
+    dt: torch.Tensor
+    y0: torch.Tensor
+    y1: torch.Tensor
+
+
+class Euler(SingleStepMethod[None, LinearInterpolationData]):
+    """Forward Euler, no error estimate, linear dense output (single_step_methods/euler.py:22-84)."""
+
+    def __init__(self, term: Optional[ODETerm]):
+        super().__init__()
+        self.term = term
+        self._cab = EULER.to_cabi(_cabi.INTERP_DOPRI5, 1)
+
+    def init(self, term, problem, f0, *, stats, args):
+        return None
+
+    def step(self, term, running, y0, t0, dt, state, *, stats, args):
+        term_ = self.term if term is None else term
+        assert term_ is not None
+        k0 = term_.vf(t0, y0, stats, args)
+        y1 = _launch.erk_stage(self._cab, 1, y0, dt, [k0])  # y0 + dt * k0 (euler.py:62)
+        return StepResult(y1, None), LinearInterpolationData(t0, dt, y0, y1), state, None
+
+    def merge_states(self, accept, current, previous):
+        return None
+
+    def convergence_order(self):
+        return 1
+
+    def build_interpolation(self, data: LinearInterpolationData):
+        return LinearInterpolation(data.t0, data.dt, data.y0, data.y1)

@@ -148,3 +148,9 @@ TSIT5 = ButcherTableau.from_lists(
          47.37952196281928252, -34.87065786149661051, 2.5],
     ],
 )
+
+# Heun's method (explicit trapezoidal rule) with the embedded Euler step as error estimate.
+HEUN = ButcherTableau.from_lists(c=[0.0, 1.0], a=[[], [1.0]], b=[0.5, 0.5], b_low_order=[1.0, 0.0])
+
+# Forward Euler written as a 2-node tableau: its single stage combination y0 + dt * k0 is the step.
+EULER = ButcherTableau.from_lists(c=[0.0, 1.0], a=[[], [1.0]], b=[1.0, 0.0], b_err=[0.0, 0.0])
