@@ -82,3 +82,51 @@ def test_backsolve_forward_uses_the_fused_kernel_for_builtin_fields():
         a = plain.solve(to.InitialValueProblem(yp, t0, t1)).ys[:, -1].sum(dim=1)
         b = plain.solve(to.InitialValueProblem(y0.detach(), t0, t1)).ys[:, -1].sum(dim=1)
     assert torch.allclose((a - b) / eps, gy[:, 0], rtol=1e-3, atol=1e-5)
+
+
+class TanhField(torch.nn.Module):
+    """Same module as tests/golden/make_golden_backsolve.py (parameters loaded from the fixture)."""
+
+    def __init__(self, n, hidden):
+        super().__init__()
+        self.l1 = torch.nn.Linear(n, hidden).double()
+        self.l2 = torch.nn.Linear(hidden, n).double()
+
+    def forward(self, t, y):
+        return self.l2(torch.tanh(self.l1(y))) * (1 + 0.1 * torch.sin(t)[..., None])
+
+
+@pytest.mark.parametrize("name,cls", [("backsolve", to.BacksolveAdjoint), ("joint", to.JointBacksolveAdjoint)])
+@pytest.mark.parametrize("with_t_eval", [False, True])
+def test_gradients_match_the_reference_golden(name, cls, with_t_eval):
+    """Gradients of the REAL reference's adjoints (CPU fp64, tests/golden/backsolve_gradients.npz)."""
+    import os
+
+    import numpy as np
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "backsolve_gradients.npz"))
+    B, n = z["y0"].shape
+    model = TanhField(n, 8)
+    with torch.no_grad():
+        for i, p in enumerate(model.parameters()):
+            p.copy_(torch.from_numpy(z[f"param{i}"]))
+    model = model.to(DEV)
+    y0 = torch.from_numpy(z["y0"]).to(DEV).requires_grad_()
+    w = torch.from_numpy(z["w"]).to(DEV)
+    term = to.ODETerm(model)
+    adj = cls(term, to.Tsit5(term), to.IntegralController(1e-9, 1e-9, term=term))
+    if with_t_eval:
+        t_eval = torch.linspace(0.0, 2.0, 5, dtype=torch.float64, device=DEV).repeat(B, 1)
+        sol = adj.solve(to.InitialValueProblem(y0, t_eval=t_eval))
+        loss = (sol.ys[:, -1] * w).sum() + (sol.ys[:, 2] ** 2).sum()
+    else:
+        sol = adj.solve(to.InitialValueProblem(y0, torch.zeros(B, dtype=torch.float64, device=DEV),
+                                               torch.full((B,), 2.0, dtype=torch.float64, device=DEV)))
+        loss = (sol.ys[:, -1] * w).sum()
+    key = f"{name}_{'teval' if with_t_eval else 'tend'}"
+    assert np.allclose(sol.ys.detach().cpu().numpy(), z[f"{key}_ys"], rtol=1e-7, atol=1e-9)
+    assert abs(float(loss) - float(z[f"{key}_loss"])) <= 1e-7 * abs(float(z[f"{key}_loss"]))
+    grads = torch.autograd.grad(loss, [y0] + list(model.parameters()))
+    assert np.allclose(grads[0].cpu().numpy(), z[f"{key}_grad_y0"], rtol=1e-6, atol=1e-8)
+    for i, gp in enumerate(grads[1:]):
+        assert np.allclose(gp.cpu().numpy(), z[f"{key}_grad_p{i}"], rtol=1e-6, atol=1e-8), f"param {i}"
