@@ -27,5 +27,11 @@ for fn, name in ((lambda: f(None, y), "tcgen05 kernel"), (torch_bf16, "torch bf1
     e0.record()
     for _ in range(20): fn()
     e1.record(); torch.cuda.synchronize()
-    print(name, e0.elapsed_time(e1) / 20 * 1e3, "us per eval (B=8192)")
+    print(name, e0.elapsed_time(e1) / 20 * 1e3, "us per eval (B=8192), eager launches")
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(20): fn()
+    g.replay(); torch.cuda.synchronize()
+    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+    print(name, e0.elapsed_time(e1) / 20 * 1e3, "us per eval (B=8192), CUDA-graph replay of 20")
 PY

@@ -19,14 +19,14 @@ namespace mlp {
 
 constexpr int kWidth = 256;
 constexpr int kBM = 128;                       // rows per CTA (UMMA M)
-constexpr int kThreads = 256;                  // 8 warps: 4 TMEM lane quarters x 2 column halves
+constexpr int kThreads = 512;                  // 16 warps: 4 TMEM lane quarters x 4 column quarters
 constexpr int kKBlock = 64;                    // bf16 elements per 128-byte swizzle row
 constexpr int kNumKBlocks = kWidth / kKBlock;  // 4
 constexpr int kABlockBytes = kBM * 128;        // 16 KB per K-block of the activation tile
 constexpr int kWBlockBytes = kWidth * 128;     // 32 KB per K-block of the weight tile
 constexpr int kSmemA = kNumKBlocks * kABlockBytes;  // 64 KB
 constexpr int kSmemW = kNumKBlocks * kWBlockBytes;  // 128 KB
-constexpr int kSmemBytes = kSmemA + kSmemW + kWidth * 4 + 64 + 1024;  // + bias + barrier + alignment slack
+constexpr int kSmemBytes = kSmemA + kSmemW + kWidth * 4 + 64;  // + bias + barrier / TMEM slot
 constexpr uint32_t kTmemCols = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -86,8 +86,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict__ weights,
                    const float* __restrict__ biases, float* __restrict__ out, long long B, int n_layers) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (SWIZZLE_128B atoms) is requested from the compiler / driver; no integer
+  // round-up, so that the compiler keeps these pointers in the shared address space (LDS/STS)
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = smem + kSmemA;
   float* sBias = reinterpret_cast<float*>(smem + kSmemA + kSmemW);
@@ -125,11 +126,12 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
 
   // ---- activation tile: fp32 rows of y -> bf16, swizzled K-major (rows past B are zero) ----
   constexpr int kAChunks = kBM * (kWidth / 8);  // 4096 chunks of 8 elements, 16 per thread
+  constexpr int kAU = 8;                        // chunks in flight per thread (16 x 16-byte loads)
 #pragma unroll 1
-  for (int base = 0; base < kAChunks; base += kThreads * 4) {
-    float4 v0[4], v1[4];
+  for (int base = 0; base < kAChunks; base += kThreads * kAU) {
+    float4 v0[kAU], v1[kAU];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {  // all loads first (memory-level parallelism)
+    for (int u = 0; u < kAU; ++u) {  // all loads first (memory-level parallelism)
       const int idx = base + u * kThreads + tid;
       const int row = idx / (kWidth / 8), chunk = idx % (kWidth / 8);
       v0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -141,7 +143,7 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kAU; ++u) {
       const int idx = base + u * kThreads + tid;
       const int row = idx / (kWidth / 8), chunk = idx % (kWidth / 8);
       uint4 p;
@@ -192,12 +194,12 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
     if (layer + 1 < n_layers) load_weights_async(layer + 1);
 
     // ---- epilogue: TMEM -> registers, + bias, tanh, -> next layer's activation tile / out ----
-    const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter, column half
+    const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter
     const int row = q * 32 + lane;
     const bool last = layer == n_layers - 1;
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-      const int n0 = half * 128 + j * 32;
+    for (int j = 0; j < 2; ++j) {
+      const int n0 = cq * 64 + j * 32;
       uint32_t r[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0;
       asm volatile(
@@ -231,10 +233,24 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
           p.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
           *reinterpret_cast<uint4*>(sA + swz(kABlockBytes, n >> 6, row, (n & 63) >> 3)) = p;
         }
-      } else if (m0 + row < B) {
-        float4* dst = reinterpret_cast<float4*>(out + (m0 + row) * kWidth + n0);
+      } else {
+        // last layer: stage the fp32 tile in the (now idle) weight buffer, XOR-swizzled by row so
+        // that neither these per-row writes nor the per-column reads below conflict on a bank
+        float* sOut = reinterpret_cast<float*>(sW);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        for (int i = 0; i < 32; ++i) sOut[row * kWidth + ((n0 + i) ^ (row & 31))] = v[i];
+      }
+    }
+    if (last) {
+      __syncthreads();
+      // coalesced copy-out: one warp writes whole 1 KB rows, 128 contiguous bytes per instruction
+      const float* sOut = reinterpret_cast<const float*>(sW);
+      for (int r = warp; r < kBM; r += kThreads / 32) {
+        if (m0 + r < B) {
+          float* dst = out + (m0 + r) * kWidth;
+#pragma unroll
+          for (int j = 0; j < kWidth / 32; ++j) dst[lane + 32 * j] = sOut[r * kWidth + ((lane + 32 * j) ^ (r & 31))];
+        }
       }
     }
     // TMEM reads and smem writes of this layer are done before the next layer's MMA starts
