@@ -30,7 +30,7 @@ CHAOTIC = ["c3_lv_f32_dopri5", "lv_f32_tsit5_pid", "lv_data32_time64", "linear_f
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not p.endswith("tableaus.npz"))
+                  if not p.endswith(("tableaus.npz", "_gradients.npz")))
 
 
 def load_case(name):

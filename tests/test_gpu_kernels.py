@@ -343,18 +343,6 @@ def test_extra_args_reach_f_by_identity():
     assert len(seen) >= 8 and all(a is marker for a in seen)
 
 
-def test_grad_requiring_inputs_are_refused_loudly():
-    lin = torch.nn.Linear(2, 2).to(DEV)
-    term = to.ODETerm(lambda t, y: lin(y))
-    term.lin = lin
-    solver = to.AutoDiffAdjoint(to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term))
-    prob = to.InitialValueProblem(torch.ones(3, 2, device=DEV), torch.zeros(3, device=DEV), torch.ones(3, device=DEV))
-    with pytest.raises(NotImplementedError, match="forward-only"):
-        solver.solve(prob)
-    with torch.no_grad():
-        assert (solver.solve(prob).status == 0).all()
-
-
 def test_cuda_graph_replay_of_the_staged_iteration_is_bit_identical():
     rng = np.random.default_rng(11)
     B = 257

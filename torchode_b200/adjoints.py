@@ -87,9 +87,12 @@ class AutoDiffAdjoint(nn.Module):
         _launch.require_cuda(problem.y0, problem.t_start, problem.t_end, problem.t_eval, dt0)
         if torch.is_grad_enabled() and (
                 problem.y0.requires_grad or any(p.requires_grad for p in term_.parameters())):
-            raise NotImplementedError(
-                "the CUDA solve loop is forward-only: wrap the call in torch.no_grad() (autograd "
-                "through the fused kernels is not implemented yet)")
+            # forward = the CUDA loop (recorded), backward = recompute-based (autodiff.py)
+            if problem.batch_size == 0:
+                return self._empty_solution(problem, term_)
+            from .autodiff import solve_with_grad
+
+            return solve_with_grad(self, problem, term_, dt0, args)
         if problem.batch_size == 0:
             return self._empty_solution(problem, term_)
         with torch.no_grad(), torch.cuda.device(problem.device):
@@ -178,7 +181,7 @@ class AutoDiffAdjoint(nn.Module):
     # ------------------------------------------------------------------------------------
     # route 2: stage-wise kernels around an opaque f
     # ------------------------------------------------------------------------------------
-    def _solve_staged(self, problem, term_, dt0, args, general: bool = False) -> Solution:
+    def _solve_staged(self, problem, term_, dt0, args, general: bool = False, record=None) -> Solution:
         lib = _cabi.lib()
         method, ctrl = self.step_method, self.step_size_controller
         dev, D, Tt = problem.device, problem.data_dtype, problem.time_dtype
@@ -187,7 +190,7 @@ class AutoDiffAdjoint(nn.Module):
         cab_c = ctrl.to_cabi(method.convergence_order(), D, self.max_steps)
         S = cab_t.n_stages
         plan = None
-        if self.use_cuda_graph:
+        if self.use_cuda_graph and record is None:
             te = problem.t_eval
             key = (str(dev), B, F, Tn, D, Tt, general, id(term_.f), id(args), dt0 is None,
                    None if te is None else (te.stride(0) == 0), bytes(cab_t), bytes(cab_c))
@@ -262,6 +265,8 @@ class AutoDiffAdjoint(nn.Module):
         ctl_host = None
         graph = plan["graph"] if plan is not None else None
         while True:
+            if record is not None:
+                record.snapshot(st)
             if graph is not None:
                 graph.replay()
             else:
@@ -279,13 +284,18 @@ class AutoDiffAdjoint(nn.Module):
                 ctl_host = pinned[old].tolist()
                 if ctl_host[_cabi.CTL_NONMONO] and not general and Tn:
                     # t_eval rows are not monotone in time: redo with the scan-all mask
-                    return self._solve_staged(problem, term_, dt0, args, general=True)
+                    if record is not None:
+                        record.snaps.clear()
+                    return self._solve_staged(problem, term_, dt0, args, general=True, record=record)
                 if ctl_host[_cabi.CTL_STOP]:
                     break
         torch.cuda.current_stream(dev).synchronize()
         ctl_host = st.ctl.tolist()
         iters = ctl_host[_cabi.CTL_ITERS]
+        if record is not None:
+            record.snapshot(st)  # state after the last iteration
         self.last_run = {"route": "staged+graph" if graph is not None else "staged", "iterations": iters,
+                         "general": general,
                          "iterations_launched": launched,
                          # 6 stage kernels + finish (3 launches in split mode) per launched iteration, + init
                          "kernel_launches_min": launched * S + (2 if dt0 is None else 1)}
