@@ -274,6 +274,13 @@ int tode_mlp_tanh256_forward(const void* y, const void* weights_bf16, const void
 int64_t tode_bench_fp64_fma_threads(void);
 int tode_bench_fp64_fma(int64_t iters, void* sink, int64_t* n_fma_out, void* stream);
 
+/* Test aid (not on the solve path): checks on `n` pseudo-random and adversarial operands that
+ * the branch-free scalar functions of the fused kernel (division, log2, exp2, controller) return
+ * the bits of the checked functions wherever their range flag stays set.  counts8: 8 x uint64
+ * on the device, zeroed by the caller; [0..3] receive the number of mismatches per function,
+ * [4..7] how often the fast flag stayed set. */
+int tode_selftest_fast_math(int64_t n, uint64_t seed, const tode_controller* ctrl, void* counts8, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -494,3 +494,18 @@ def test_edge_cases_empty_batch_zero_span_and_strided_inputs(staged):
         one = solver.solve(to.InitialValueProblem(y0_view[:1], torch.zeros(1, device=DEV),
                                                   torch.tensor(2.0, device=DEV).expand(1)))
         assert one.ys.shape == (1, 1, 2) and (one.status == 0).all() and torch.isfinite(one.ys).all()
+
+
+def test_fast_scalar_math_is_bit_identical():
+    """The fused kernel's branch-free division / log2 / exp2 / controller must return the bits
+    of the checked functions wherever they leave their range flag set (erk_math.cuh)."""
+    lib = _cabi.lib()
+    ctrl = to.PIDController(1e-8, 1e-8, 0.2, 0.5, 0.1).to_cabi(5, torch.float64)
+    counts = torch.zeros(8, dtype=torch.int64, device="cuda")
+    n = 1 << 26
+    _cabi.check(lib.tode_selftest_fast_math(n, 20241017, C.byref(ctrl), counts.data_ptr(),
+                                            _launch.stream_ptr(counts.device)), "selftest")
+    got = counts.tolist()
+    assert got[:4] == [0, 0, 0, 0], f"mismatches (div, log2, exp2, controller): {got[:4]}"
+    # the fast path must actually have been exercised: most moderate-range operands keep the flag
+    assert got[4] > n // 4 and got[5] > n // 4 and got[6] > n // 8 and got[7] > n // 16, got

@@ -33,6 +33,21 @@ from .terms import ODETerm
 _INT32_MAX = 2**31 - 1
 
 
+def _uniform_stats(term_, problem, stats: Dict[str, Any], n_f_evals: int):
+    """``term.init`` for a solve whose evaluation count is known in one piece (the CUDA routes
+    count loop iterations on the device): the same (B,) CPU int64 ``n_f_evals`` as ``init`` followed
+    by ``n`` calls of ``vf`` (terms.py:42-58), but as a stride-0 expansion of one element -- zeros +
+    fill of the literal tensor cost milliseconds of host time at B = 2^20..2^24, in which the GPU
+    idles.  A term subclass may track more than the plain ODETerm: it keeps its own protocol."""
+    if type(term_) is ODETerm:
+        if term_.with_stats:
+            stats["n_f_evals"] = torch.full((1,), n_f_evals, dtype=torch.long).expand(problem.batch_size)
+        return
+    term_.init(problem, stats)
+    if "n_f_evals" in stats:
+        stats["n_f_evals"].fill_(n_f_evals)
+
+
 class AutoDiffAdjoint(nn.Module):
     def __init__(self, step_method: SingleStepMethod, step_size_controller: StepSizeController, *,
                  max_steps: Optional[int] = None, backprop_through_step_size_control: bool = True):
@@ -170,10 +185,8 @@ class AutoDiffAdjoint(nn.Module):
             iters, _, _, _ = run(first_fail)
             self.last_run = {"route": "fused+replay", "kernel_launches": 4, "iterations": iters}
         stats: Dict[str, Any] = {}
-        term_.init(problem, stats)
-        if "n_f_evals" in stats:
-            n_stage_evals = cab_t.n_stages - 1  # FSAL
-            stats["n_f_evals"].fill_((2 if dt0 is None else 1) + n_stage_evals * iters)
+        n_stage_evals = cab_t.n_stages - 1  # FSAL
+        _uniform_stats(term_, problem, stats, (2 if dt0 is None else 1) + n_stage_evals * iters)
         stats["n_steps"], stats["n_accepted"], stats["n_initialized"] = n_steps, n_accepted, n_init
         ts = problem.t_eval if problem.t_eval is not None else problem.t_end[:, None]
         return Solution(ts=ts, ys=ys, stats=stats, status=status)
@@ -209,10 +222,17 @@ class AutoDiffAdjoint(nn.Module):
         stream = _launch.stream_ptr(dev)
         tab_p, ctrl_p, st_p = C.byref(cab_t), C.byref(cab_c), C.byref(st.c)
         stats: Dict[str, Any] = {}
-        term_.init(problem, stats)
+        plain_term = type(term_) is ODETerm
+        if plain_term:
+            # the per-call ``n_f_evals += 1`` of terms.py:58 on a 1-element stand-in (an O(B) host
+            # pass per f call otherwise); the (B,) tensor is produced once at the end
+            call_stats = {"n_f_evals": torch.zeros(1, dtype=torch.long)} if term_.with_stats else {}
+        else:
+            term_.init(problem, stats)
+            call_stats = stats
 
         def vf(t, y):
-            out = term_.vf(t, y, stats, args)
+            out = term_.vf(t, y, call_stats, args)
             if out.dtype != D:
                 raise TypeError(f"f returned {out.dtype}, expected the dtype of y0 ({D})")
             if not out.is_contiguous() or out.data_ptr() % 16:
@@ -299,8 +319,10 @@ class AutoDiffAdjoint(nn.Module):
                          "iterations_launched": launched,
                          # 6 stage kernels + finish (3 launches in split mode) per launched iteration, + init
                          "kernel_launches_min": launched * S + (2 if dt0 is None else 1)}
-        if "n_f_evals" in stats:
-            # speculative iterations after the stop flag are no-ops on the device
+        # speculative iterations after the stop flag are no-ops on the device
+        if plain_term:
+            _uniform_stats(term_, problem, stats, n_init_evals + (S - 1) * iters)
+        elif "n_f_evals" in stats:
             stats["n_f_evals"].fill_(n_init_evals + (S - 1) * iters)
         stats["n_steps"] = st.n_steps.to(torch.long)
         stats["n_accepted"] = st.n_accepted.to(torch.long)

@@ -52,6 +52,23 @@ struct Field<TODE_FIELD_LOTKA_VOLTERRA, D, 2> {
   }
 };
 
+template <typename D, int F>
+struct Row {
+  D v[F];
+};
+
+// Error ratio + controller through the checked (branching) functions: the rarely taken second
+// opinion of the fused kernel's branch-free step (zero error, non-finite values, ...).
+template <typename D, typename T, int F>
+__device__ __noinline__ CtrlOut<D, T> error_control_checked(const CtrlP<D, T>& c, Row<D, F> aerr, Row<D, F> bounds,
+                                                            T dt, D r1, D r2, double L1, double L2) {
+  D q[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) q[f] = fdiv(aerr.v[f], bounds.v[f]);
+  double Lr;
+  return controller_l<D, T>(c, row_norm_small<D, F>(q, c.norm), dt, r1, r2, L1, L2, &Lr);
+}
+
 template <typename D, typename T>
 struct FusedArgs {
   TabP<D, T> tab;
@@ -119,7 +136,7 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
   const TabP<D, T>& tab = A.tab;
   const CtrlP<D, T>& c = A.ctrl;
   const Field<FIELD, D, F> field(A.fp);
-  const D sqrt_f = (D)sqrt((double)F);
+  const DivBy<D> div_sqrt_f((D)sqrt((double)F));
 
   int ns = 0, nacc = 0, status = TODE_SUCCESS, cur = 0, fail_iter = 0x7fffffff, nonmono = 0;
   if (valid) {
@@ -199,17 +216,21 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
         }
         field(y1, k[i]);
       }
-      // error ratio (runge_kutta.py:269, step_size_controllers.py:394-400)
-      D q[F];
+      // error ratio (runge_kutta.py:269, step_size_controllers.py:394-400) and controller: first
+      // without branches (erk_math.cuh "fast path"); if any of its range flags is cleared, once
+      // more through the checked functions
+      Row<D, F> aerr, bounds;
 #pragma unroll
       for (int f = 0; f < F; ++f) {
         D ks[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) ks[s] = k[s][f];
-        const D err = weighted_sum<D, S>(dtD, tab.b_err, ks);
-        const D bounds = ffma(c.rtol, max_nan_nn(fabs_(y[f]), fabs_(y1[f])), c.atol);
-        q[f] = fdiv(fabs_(err), bounds);
+        aerr.v[f] = fabs_(weighted_sum<D, S>(dtD, tab.b_err, ks));
+        bounds.v[f] = ffma(c.rtol, max_nan_nn(fabs_(y[f]), fabs_(y1[f])), c.atol);
       }
+      bool ok = true;
+      D q[F];
+      div_chk_n<F>(aerr.v, bounds.v, q, ok);
       D nrm;
       if (c.norm == TODE_NORM_MAX) {
         nrm = fabs_(q[0]);
@@ -218,11 +239,11 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
       } else {
         D v[F];
 #pragma unroll
-        for (int f = 0; f < F; ++f) v[f] = fdiv(q[f], sqrt_f);
+        for (int f = 0; f < F; ++f) v[f] = div_sqrt_f(q[f], ok);
         nrm = fsqrt(row_sumsq_canonical<D, F>(v));
       }
-      double Lr;
-      const CtrlOut<D, T> o = controller_l<D, T>(c, nrm, dt, r1, r2, L1, L2, &Lr);
+      CtrlOut<D, T> o = controller_fast<D, T>(c, nrm, dt, r1, r2, L1, L2, ok);
+      if (!ok) o = error_control_checked<D, T, F>(c, aerr, bounds, dt, r1, r2, L1, L2);
       const bool upd = o.accept;                 // running is true inside the loop
       const T t_new = upd ? add(t, dt) : t;      // adjoints.py:151
       ns += 1;                                   // :161
@@ -279,7 +300,7 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
       if (c.pid && running_new) {                                       // :253-255
         if (o.accept) {
           L2 = L1;
-          L1 = Lr;
+          L1 = o.L_ratio;
         }
         r1 = o.r1;
         r2 = o.r2;

@@ -69,7 +69,7 @@ def gather_solution(local: Solution, global_batch: int, ts: Optional[torch.Tenso
         # longest-running one -> MAX over ranks
         n = local.stats["n_f_evals"][:1].to(ys.device, copy=True)
         dist.all_reduce(n, op=dist.ReduceOp.MAX, group=group)
-        stats["n_f_evals"] = torch.full((global_batch,), int(n.item()), dtype=torch.long)
+        stats["n_f_evals"] = torch.full((1,), int(n.item()), dtype=torch.long).expand(global_batch)
     if ts is None:
         ts = _gather_rows(local.ts, sizes, group)
     return Solution(ts=ts, ys=ys, stats=stats, status=status)
