@@ -127,10 +127,15 @@ TODE_DEV void store_row(D* p, const D* r) {
   }
 }
 
-// MINB = resident CTAs per SM the kernel is compiled for (register budget 65536 / (128 MINB))
-template <typename D, typename T, int F, int FIELD, int MINB>
+// MINB = resident CTAs per SM the kernel is compiled for (register budget 65536 / (128 MINB)).
+// CK / TE = what this instantiation knows about the problem at compile time (state that is never
+// used costs registers, and at 6 CTAs / SM the fp64 kernel has none to spare): CK 0 = integral
+// controller, 1 = PID without derivative term (no r2 / L2), 2 = any; TE false = no t_eval.
+// <2, true> handles every problem; the launcher picks the tightest instantiation that exists.
+template <typename D, typename T, int F, int FIELD, int MINB, int CK, bool TE>
 __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_constant__ FusedArgs<D, T> A) {
   constexpr int S = kStagesFused;
+  const long long Tn = TE ? A.Tn : 0;
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = b < A.B;
   const TabP<D, T>& tab = A.tab;
@@ -145,8 +150,8 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
     const T ts = A.t_start[b], te = A.t_end[b];
     const T dir = dir_of(ts, te);
     const T t_min = ts < te ? ts : te, t_max = ts < te ? te : ts;
-    const T* tev = A.Tn > 0 ? A.t_eval + b * A.te_stride : nullptr;
-    D* ye = A.ys + b * (A.Tn > 0 ? A.Tn : 1) * F;
+    const T* tev = Tn > 0 ? A.t_eval + b * A.te_stride : nullptr;
+    D* ye = A.ys + b * (Tn > 0 ? Tn : 1) * F;
     T t = ts, dt;
     field(y, k[0]);  // controller.init / ExplicitRungeKutta.init: f0 = f(t_start, y0)
 
@@ -186,12 +191,12 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
     dt = clamp_nan(dt, sub(t_min, t), sub(t_max, t));  // adjoints.py:109
 
     // ---- evaluation exactly at t_start, monotonicity of the t_eval row -------------------
-    if (A.Tn > 0) {
+    if (Tn > 0) {
       if (tev[0] == ts) {  // adjoints.py:123-126
         store_row<D, F>(ye, y);
         cur = 1;
       }
-      for (long long j = 1; j < A.Tn; ++j)
+      for (long long j = 1; j < Tn; ++j)
         if (mul(dir, tev[j]) < mul(dir, tev[j - 1])) nonmono = 1;
     } else {
       store_row<D, F>(ye, y);  // never hand out uninitialised memory
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
         for (int f = 0; f < F; ++f) v[f] = div_sqrt_f(q[f], ok);
         nrm = fsqrt(row_sumsq_canonical<D, F>(v));
       }
-      CtrlOut<D, T> o = controller_fast<D, T>(c, nrm, dt, r1, r2, L1, L2, ok);
+      CtrlOut<D, T> o = controller_fast<D, T, CK>(c, nrm, dt, r1, r2, L1, L2, ok);
       if (!ok) o = error_control_checked<D, T, F>(c, aerr, bounds, dt, r1, r2, L1, L2);
       const bool upd = o.accept;                 // running is true inside the loop
       const T t_new = upd ? add(t, dt) : t;      // adjoints.py:151
@@ -272,13 +277,13 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
         for (int f = 0; f < F; ++f) out[f] = horner4<D>(co[f], x);
         store_row<D, F>(dst, out);
       };
-      if (A.Tn == 0) {
+      if (Tn == 0) {
         // the interpolant of the sample's LAST loop iteration, evaluated at t_end: the
         // iteration in which it finishes, fails, or the batch is cut off (iter_cap)
         if (!running_new || status != TODE_SUCCESS || (A.iter_cap > 0 && ns >= A.iter_cap))
           eval_at(te, ye);
       } else {
-        while (cur < A.Tn) {
+        while (cur < Tn) {
           const T tq = tev[cur];
           if (!(ffma(dir, t_new, mul(-dir, tq)) >= (T)0)) break;
           eval_at(tq, ye + (long long)cur * F);
@@ -297,13 +302,13 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
       t = t_new;
       T dt_new = running_new ? o.dt_next : dt;                          // :247
       dt = clamp_nan(dt_new, sub(t_min, t_new), sub(t_max, t_new));     // :251
-      if (c.pid && running_new) {                                       // :253-255
+      if (CK >= 1 && c.pid && running_new) {                            // :253-255
         if (o.accept) {
-          L2 = L1;
+          if (CK >= 2) L2 = L1;
           L1 = o.L_ratio;
         }
         r1 = o.r1;
-        r2 = o.r2;
+        if (CK >= 2) r2 = o.r2;
       }
       running = running_new;
       if (status != TODE_SUCCESS) fail_iter = ns;
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
 
     A.n_steps[b] = ns;
     A.n_accepted[b] = nacc;
-    A.n_initialized[b] = A.Tn > 0 ? cur : 1;
+    A.n_initialized[b] = Tn > 0 ? cur : 1;
     A.status[b] = status;
     if (A.t_final != nullptr) A.t_final[b] = t;
     if (A.dt_final != nullptr) A.dt_final[b] = dt;
