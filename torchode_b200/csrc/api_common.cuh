@@ -54,6 +54,22 @@ inline CtrlP<D, T> make_ctrl(const tode_controller* c) {
   return p;
 }
 
+// same values as kLogPoly / kExpPoly / kPowConst (erk_math.cuh)
+inline PowTab make_powtab() {
+  PowTab t{};
+  for (int i = 0; i < 11; ++i) t.logp[i] = 1.0 / (double)(23 - 2 * i);
+  double fact = 87178291200.0;  // 14!
+  for (int i = 0; i < 15; ++i) {
+    t.expp[i] = 1.0 / fact;
+    if (14 - i > 0) fact /= (double)(14 - i);
+  }
+  t.c[0] = 1.4142135623730951;
+  t.c[1] = 1.4426950408889634;
+  t.c[2] = 0.6931471805599453;
+  t.c[3] = 18014398509481984.0;
+  return t;
+}
+
 inline int sm_count() {
   static int cached = 0;
   if (cached == 0) {

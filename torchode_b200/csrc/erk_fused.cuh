@@ -73,6 +73,7 @@ template <typename D, typename T>
 struct FusedArgs {
   TabP<D, T> tab;
   CtrlP<D, T> ctrl;
+  PowTab pow;
   double fp[TODE_MAX_FIELD_PARAMS];
   long long B, Tn;
   const D* y0;
@@ -205,8 +206,11 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
     D r1 = (D)1, r2 = (D)1;
     double L1 = 0.0, L2 = 0.0;  // log2 of the PID history, carried instead of recomputed (same bits)
     bool running = true;
+    // the step counter is 32-bit: limits beyond INT_MAX can never be reached
+    const int iter_cap = (A.iter_cap > 0 && A.iter_cap < 0x7fffffffLL) ? (int)A.iter_cap : 0x7fffffff;
+    const int max_steps = (c.max_steps >= 0 && c.max_steps < 0x7fffffffLL) ? (int)c.max_steps : 0x7fffffff;
     // ---- the loop (adjoints.py:135-260) ---------------------------------------------------
-    while (running && status == TODE_SUCCESS && (A.iter_cap <= 0 || ns < A.iter_cap)) {
+    while (running && status == TODE_SUCCESS && ns < iter_cap) {
       const D dtD = (D)dt;  // runge_kutta.py:247
       D y1[F];
 #pragma unroll
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
 #pragma unroll
         for (int s = 0; s < S; ++s) ks[s] = k[s][f];
         aerr.v[f] = fabs_(weighted_sum<D, S>(dtD, tab.b_err, ks));
-        bounds.v[f] = ffma(c.rtol, max_nan_nn(fabs_(y[f]), fabs_(y1[f])), c.atol);
+        bounds.v[f] = ffma(c.rtol, max_abs_nan(y[f], y1[f]), c.atol);
       }
       bool ok = true;
       D q[F];
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
         for (int f = 0; f < F; ++f) v[f] = div_sqrt_f(q[f], ok);
         nrm = fsqrt(row_sumsq_canonical<D, F>(v));
       }
-      CtrlOut<D, T> o = controller_fast<D, T, CK>(c, nrm, dt, r1, r2, L1, L2, ok);
+      CtrlOut<D, T> o = controller_fast<D, T, CK>(c, nrm, dt, r1, r2, L1, L2, ok, A.pow);
       if (!ok) o = error_control_checked<D, T, F>(c, aerr, bounds, dt, r1, r2, L1, L2);
       const bool upd = o.accept;                 // running is true inside the loop
       const T t_new = upd ? add(t, dt) : t;      // adjoints.py:151
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
       nacc += upd ? 1 : 0;                       // :162
       const bool running_new = ffma(dir, t_new, mul(-dir, te)) < (T)0;  // :169
       status = o.status;                         // :171-181
-      if (c.max_steps >= 0 && (long long)ns >= c.max_steps) status = TODE_REACHED_MAX_STEPS;
+      if (ns >= max_steps) status = TODE_REACHED_MAX_STEPS;
 
       // ---- dense output (adjoints.py:215-234, 298-301) ------------------------------------
       bool have_co = false;
@@ -280,7 +284,7 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
       if (Tn == 0) {
         // the interpolant of the sample's LAST loop iteration, evaluated at t_end: the
         // iteration in which it finishes, fails, or the batch is cut off (iter_cap)
-        if (!running_new || status != TODE_SUCCESS || (A.iter_cap > 0 && ns >= A.iter_cap))
+        if (!running_new || status != TODE_SUCCESS || ns >= iter_cap)
           eval_at(te, ye);
       } else {
         while (cur < Tn) {

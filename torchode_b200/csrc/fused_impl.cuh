@@ -54,6 +54,7 @@ int launch_fused(int field, const double* fp, const tode_tableau* tab, const tod
   FusedArgs<D, T> a{};
   a.tab = make_tab<D, T>(tab);
   a.ctrl = make_ctrl<D, T>(ctrl);
+  a.pow = make_powtab();
   for (int i = 0; i < TODE_MAX_FIELD_PARAMS; ++i) a.fp[i] = fp[i];
   a.B = prob->B;
   a.Tn = prob->T;

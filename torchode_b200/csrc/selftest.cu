@@ -53,7 +53,7 @@ __device__ __forceinline__ bool same_bits(double a, double b) {
 // counts[0..3]: mismatches of division / log2 / exp2 / controller; counts[4..7]: how often the
 // fast flag stayed set (so a test can tell that the fast path was actually exercised)
 __global__ void selftest_kernel(long long n, unsigned long long seed, CtrlP<double, double> c,
-                                unsigned long long* counts) {
+                                const __grid_constant__ PowTab pt, unsigned long long* counts) {
   unsigned long long bad[4] = {0, 0, 0, 0}, used[4] = {0, 0, 0, 0};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -78,14 +78,14 @@ __global__ void selftest_kernel(long long n, unsigned long long seed, CtrlP<doub
     {  // log2
       bool ok = true;
       const double x = fabs(a);
-      const double l = det_log2_fast(x, ok);
+      const double l = det_log2_fast(x, ok, pt);
       if (ok) { used[1]++; if (!same_bits(l, det_log2_safe(x))) bad[1]++; }
     }
     {  // exp2 (arguments mostly in the useful range)
       const double z[3] = {mode == 1 ? a * 1e-9 : a, ldexp(gen(h2, 1), -30), gen(h3, mode)};
       double p[3];
       bool ok = true;
-      det_exp2_fast<3>(z, p, ok);
+      det_exp2_fast<3>(z, p, ok, pt);
       if (ok) {
         used[2]++;
         for (int j = 0; j < 3; ++j)
@@ -103,7 +103,7 @@ __global__ void selftest_kernel(long long n, unsigned long long seed, CtrlP<doub
       cc.pid = (int)((h2 >> 20) & 1);
       if ((h2 >> 21) & 1) cc.e_prev2 = 0.0;
       bool ok = true;
-      const CtrlOut<double, double> f = controller_fast<double, double>(cc, nrm, dt, r1, r2, L1, L2, ok);
+      const CtrlOut<double, double> f = controller_fast<double, double>(cc, nrm, dt, r1, r2, L1, L2, ok, pt);
       if (ok) {
         used[3]++;
         double Lr;
@@ -129,6 +129,6 @@ extern "C" int tode_selftest_fast_math(int64_t n, uint64_t seed, const tode_cont
   if (n <= 0 || !ctrl || !counts8) return TODE_EINVAL;
   const tode::CtrlP<double, double> c = tode::make_ctrl<double, double>(ctrl);
   tode::selftest_kernel<<<tode::sm_count() * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      (long long)n, (unsigned long long)seed, c, static_cast<unsigned long long*>(counts8));
+      (long long)n, (unsigned long long)seed, c, tode::make_powtab(), static_cast<unsigned long long*>(counts8));
   return tode::launch_status();
 }
