@@ -11,6 +11,10 @@
 namespace tode {
 
 constexpr int kStagesFused = TODE_MAX_STAGES;  // Dopri5 and Tsit5 both have 7 stages
+#ifndef TODE_FUSED_THREADS
+#define TODE_FUSED_THREADS 128
+#endif
+constexpr int kFusedThreads = TODE_FUSED_THREADS;
 
 // ---- built-in fields: one IEEE rounding per op of torchode_b200/fields.py forward -----
 template <int FIELD, typename D, int F>
@@ -60,11 +64,11 @@ struct Row {
 // Error ratio + controller through the checked (branching) functions: the rarely taken second
 // opinion of the fused kernel's branch-free step (zero error, non-finite values, ...).
 template <typename D, typename T, int F>
-__device__ __noinline__ CtrlOut<D, T> error_control_checked(const CtrlP<D, T>& c, Row<D, F> aerr, Row<D, F> bounds,
+__device__ __noinline__ CtrlOut<D, T> error_control_checked(const CtrlP<D, T>& c, Row<D, F> err, Row<D, F> bounds,
                                                             T dt, D r1, D r2, double L1, double L2) {
   D q[F];
 #pragma unroll
-  for (int f = 0; f < F; ++f) q[f] = fdiv(aerr.v[f], bounds.v[f]);
+  for (int f = 0; f < F; ++f) q[f] = fdiv(fabs_(err.v[f]), bounds.v[f]);
   double Lr;
   return controller_l<D, T>(c, row_norm_small<D, F>(q, c.norm), dt, r1, r2, L1, L2, &Lr);
 }
@@ -134,7 +138,7 @@ TODE_DEV void store_row(D* p, const D* r) {
 // controller, 1 = PID without derivative term (no r2 / L2), 2 = any; TE false = no t_eval.
 // <2, true> handles every problem; the launcher picks the tightest instantiation that exists.
 template <typename D, typename T, int F, int FIELD, int MINB, int CK, bool TE>
-__global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_constant__ FusedArgs<D, T> A) {
+__global__ void __launch_bounds__(kFusedThreads, MINB) solve_fused_kernel(const __grid_constant__ FusedArgs<D, T> A) {
   constexpr int S = kStagesFused;
   const long long Tn = TE ? A.Tn : 0;
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -228,18 +232,18 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
       // error ratio (runge_kutta.py:269, step_size_controllers.py:394-400) and controller: first
       // without branches (erk_math.cuh "fast path"); if any of its range flags is cleared, once
       // more through the checked functions
-      Row<D, F> aerr, bounds;
+      Row<D, F> err, bounds;
 #pragma unroll
       for (int f = 0; f < F; ++f) {
         D ks[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) ks[s] = k[s][f];
-        aerr.v[f] = fabs_(weighted_sum<D, S>(dtD, tab.b_err, ks));
+        err.v[f] = weighted_sum<D, S>(dtD, tab.b_err, ks);
         bounds.v[f] = ffma(c.rtol, max_abs_nan(y[f], y1[f]), c.atol);
       }
       bool ok = true;
       D q[F];
-      div_chk_n<F>(aerr.v, bounds.v, q, ok);
+      div_chk_n<F, true>(err.v, bounds.v, q, ok);  // |err| / bounds
       D nrm;
       if (c.norm == TODE_NORM_MAX) {
         nrm = fabs_(q[0]);
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(128, MINB) solve_fused_kernel(const __grid_con
         nrm = fsqrt(row_sumsq_canonical<D, F>(v));
       }
       CtrlOut<D, T> o = controller_fast<D, T, CK>(c, nrm, dt, r1, r2, L1, L2, ok, A.pow);
-      if (!ok) o = error_control_checked<D, T, F>(c, aerr, bounds, dt, r1, r2, L1, L2);
+      if (!ok) o = error_control_checked<D, T, F>(c, err, bounds, dt, r1, r2, L1, L2);
       const bool upd = o.accept;                 // running is true inside the loop
       const T t_new = upd ? add(t, dt) : t;      // adjoints.py:151
       ns += 1;                                   // :161

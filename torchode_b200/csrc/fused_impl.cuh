@@ -19,7 +19,7 @@ __global__ void summary_init_kernel(int* summary);
 
 template <typename D, typename T, int F, int FIELD, int CK, bool TE>
 static int launch_fused_k(const FusedArgs<D, T>& a, cudaStream_t stream) {
-  constexpr int kThreads = 128;
+  constexpr int kThreads = kFusedThreads;
   summary_init_kernel<<<1, 1, 0, stream>>>(a.summary);
   const unsigned grid = (unsigned)((a.B + kThreads - 1) / kThreads);
   solve_fused_kernel<D, T, F, FIELD, TODE_FUSED_MINB, CK, TE><<<grid, kThreads, 0, stream>>>(a);
