@@ -44,6 +44,11 @@ import torchode_b200 as to  # noqa: E402
 from torchode_b200 import _cabi, _launch  # noqa: E402
 from torchode_b200.fields import LinearDecay, LotkaVolterra, VanDerPol  # noqa: E402
 
+# DRAM bytes of the dominant kernel's launch from committed ncu captures, keyed by (workload, batch)
+NCU_DRAM_BYTES = {("c2", 1 << 20): 33676544 + 18223872, ("c3", 1 << 20): 103785216 + 897567232}
+NCU_DRAM_SOURCE = {("c2", 1 << 20): "profiles/r01_ncu_fused_c2_v3.txt (outputs partly still in L2 when the launch ends)",
+                   ("c3", 1 << 20): "profiles/r01_ncu_fused_c3.txt"}
+
 METRIC = "accepted_rk_steps_per_sec"
 UNIT = "sample-steps/s"
 
@@ -640,7 +645,11 @@ def _main(out):
         "kernel": "solve_fused_kernel" if last_run.get("route", "").startswith("fused") else
                   "erk_stage_kernel x6 + erk_finish_kernel (whole staged step incl. the user's f)",
         "bound": "hbm", "achieved": alg_bytes / kernel_ms / 1e6,
-        "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / kernel_ms / 1e6 / hbm_peak, "traffic": None,
+        "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / kernel_ms / 1e6 / hbm_peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full
+        # capture of the same workload (not measurable live); known for the default workload only
+        "traffic": NCU_DRAM_BYTES.get((workload.name, B)),
+        "traffic_source": NCU_DRAM_SOURCE.get((workload.name, B)),
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
         "note": ("whole solve in registers: HBM is touched only for inputs/outputs; for C2 the kernel is "
                  "fp64-issue-bound, see fp64_issue; the HBM-bound kernels of the stage-wise path are in "
@@ -670,14 +679,17 @@ def _main(out):
         try:
             peak_fma = measure_fp64_peak(device)  # tera-FMA/s
             # fp64-pipe instructions (DFMA+DMUL+DADD+DSETP) per attempted sample-step of the fused
-            # Tsit5+PID Van der Pol kernel, from the ncu opcode mix (profiles/r01_ncu_fused_c2.txt)
-            ops_per_step = 314
+            # Tsit5+PID Van der Pol kernel, from the ncu opcode mix (profiles/r01_ncu_fused_c2_v3.txt;
+            # 314 before the branch-free scalar path)
+            ops_per_step = 251
             achieved = attempted_local / (kernel_ms * 1e-3) * ops_per_step / 1e12
             line["fp64_issue"] = {
                 "peak_tfma_per_s": peak_fma, "peak_source": "tode_bench_fp64_fma, measured live",
                 "fp64_pipe_instr_per_attempted_step": ops_per_step,
                 "achieved_tinstr_per_s": achieved, "frac": achieved / peak_fma,
-                "note": "only meaningful for the fp64 workload (c2)"}
+                "note": "only meaningful for the fp64 workload (c2); counts the lanes that carry a sample "
+                        "(a warp runs until its slowest lane is done: 92 % of the lane-steps are useful, "
+                        "the fp64 pipe itself is 73 % busy under ncu)"}
         except Exception as exc:  # measurement aid only
             line["fp64_issue"] = {"error": str(exc)}
         try:
