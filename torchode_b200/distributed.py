@@ -36,42 +36,58 @@ def shard_problem(problem: InitialValueProblem, rank: int, world_size: int) -> I
     return InitialValueProblem(problem.y0[lo:hi], problem.t_start[lo:hi], problem.t_end[lo:hi], t_eval)
 
 
-def _gather_rows(x: torch.Tensor, sizes, group) -> torch.Tensor:
-    """all_gather of row blocks that may differ by one row between ranks."""
+def _gather_rows_async(x: torch.Tensor, sizes, group):
+    """all_gather of row blocks that may differ by one row between ranks.  Returns
+    ``(work, finish)``: wait for ``work``, then ``finish()`` yields the gathered tensor."""
     world = len(sizes)
     x = x.contiguous()
     if len(set(sizes)) == 1:
         out = x.new_empty((world * sizes[0],) + tuple(x.shape[1:]))
-        dist.all_gather_into_tensor(out, x, group=group)
-        return out
+        work = dist.all_gather_into_tensor(out, x, group=group, async_op=True)
+        return work, lambda: out
     pad = max(sizes)
     padded = x.new_zeros((pad,) + tuple(x.shape[1:]))
     padded[: x.shape[0]] = x
     out = x.new_empty((world * pad,) + tuple(x.shape[1:]))
-    dist.all_gather_into_tensor(out, padded, group=group)
-    return torch.cat([out[r * pad: r * pad + n] for r, n in enumerate(sizes)])
+    work = dist.all_gather_into_tensor(out, padded, group=group, async_op=True)
+    return work, lambda: torch.cat([out[r * pad: r * pad + n] for r, n in enumerate(sizes)])
+
+
+def _gather_rows(x: torch.Tensor, sizes, group) -> torch.Tensor:
+    work, finish = _gather_rows_async(x, sizes, group)
+    work.wait()
+    return finish()
 
 
 def gather_solution(local: Solution, global_batch: int, ts: Optional[torch.Tensor] = None,
                     group=None) -> Solution:
-    """Assemble the full-batch Solution on every rank from the per-rank ones: one all_gather for
-    ``ys``, one for the stacked int64 statistics, one all_reduce(MAX) for the iteration count."""
+    """Assemble the full-batch Solution on every rank from the per-rank ones.  Every tensor is
+    gathered straight into its final buffer (no packing / unpacking passes over the gathered
+    data); the collectives are enqueued back to back and waited for once; the iteration count
+    goes through one all_reduce(MAX)."""
     world = dist.get_world_size(group)
     sizes = [hi - lo for lo, hi in (shard_bounds(global_batch, r, world) for r in range(world))]
-    ys = _gather_rows(local.ys, sizes, group)
     keys = [k for k in ("n_steps", "n_accepted", "n_initialized") if k in local.stats]
-    packed = torch.stack([local.status.to(torch.long)] + [local.stats[k].to(torch.long) for k in keys], dim=1)
-    packed = _gather_rows(packed, sizes, group)
-    status = packed[:, 0].contiguous()
-    stats = {k: packed[:, i + 1].contiguous() for i, k in enumerate(keys)}
+    pending = [_gather_rows_async(local.ys, sizes, group),
+               _gather_rows_async(local.status.to(torch.long), sizes, group)]
+    pending += [_gather_rows_async(local.stats[k].to(torch.long), sizes, group) for k in keys]
+    if ts is None:
+        pending.append(_gather_rows_async(local.ts, sizes, group))
+    n = None
     if "n_f_evals" in local.stats:
         # batch-uniform in the reference: every sample is charged the evaluations of the
         # longest-running one -> MAX over ranks
-        n = local.stats["n_f_evals"][:1].to(ys.device, copy=True)
+        n = local.stats["n_f_evals"][:1].to(local.ys.device, copy=True)
         dist.all_reduce(n, op=dist.ReduceOp.MAX, group=group)
+    for work, _ in pending:
+        work.wait()
+    gathered = [finish() for _, finish in pending]
+    ys, status = gathered[0], gathered[1]
+    stats = {k: gathered[2 + i] for i, k in enumerate(keys)}
+    if n is not None:
         stats["n_f_evals"] = torch.full((1,), int(n.item()), dtype=torch.long).expand(global_batch)
     if ts is None:
-        ts = _gather_rows(local.ts, sizes, group)
+        ts = gathered[-1]
     return Solution(ts=ts, ys=ys, stats=stats, status=status)
 
 
