@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 
 #include "erk_math.cuh"
 
@@ -54,19 +55,16 @@ inline CtrlP<D, T> make_ctrl(const tode_controller* c) {
   return p;
 }
 
-// same values as kLogPoly / kExpPoly / kPowConst (erk_math.cuh)
+// the polynomial coefficients of det_log2 / det_exp2 (pow_tables.h) for a kernel parameter block
 inline PowTab make_powtab() {
+  const unsigned long long la[6] = {TODE_POW_LOG_A1, TODE_POW_LOG_A2, TODE_POW_LOG_A3,
+                                    TODE_POW_LOG_A4, TODE_POW_LOG_A5, TODE_POW_LOG_A6};
+  const unsigned long long ee[5] = {TODE_POW_EXP_E1, TODE_POW_EXP_E2, TODE_POW_EXP_E3, TODE_POW_EXP_E4,
+                                    TODE_POW_EXP_E5};
   PowTab t{};
-  for (int i = 0; i < 11; ++i) t.logp[i] = 1.0 / (double)(23 - 2 * i);
-  double fact = 87178291200.0;  // 14!
-  for (int i = 0; i < 15; ++i) {
-    t.expp[i] = 1.0 / fact;
-    if (14 - i > 0) fact /= (double)(14 - i);
-  }
-  t.c[0] = 1.4142135623730951;
-  t.c[1] = 1.4426950408889634;
-  t.c[2] = 0.6931471805599453;
-  t.c[3] = 18014398509481984.0;
+  static_assert(sizeof(la) == sizeof(t.log_a) && sizeof(ee) == sizeof(t.exp_e), "bit patterns of doubles");
+  memcpy(t.log_a, la, sizeof(la));
+  memcpy(t.exp_e, ee, sizeof(ee));
   return t;
 }
 
