@@ -45,8 +45,8 @@ from torchode_b200 import _cabi, _launch  # noqa: E402
 from torchode_b200.fields import LinearDecay, LotkaVolterra, VanDerPol  # noqa: E402
 
 # DRAM bytes of the dominant kernel's launch from committed ncu captures, keyed by (workload, batch)
-NCU_DRAM_BYTES = {("c2", 1 << 20): 33676544 + 18223872, ("c3", 1 << 20): 103785216 + 897567232}
-NCU_DRAM_SOURCE = {("c2", 1 << 20): "profiles/r01_ncu_fused_c2_v3.txt (outputs partly still in L2 when the launch ends)",
+NCU_DRAM_BYTES = {("c2", 1 << 20): 33709056 + 10891264, ("c3", 1 << 20): 103785216 + 897567232}
+NCU_DRAM_SOURCE = {("c2", 1 << 20): "profiles/r01_ncu_fused_c2_v5.txt (outputs partly still in L2 when the launch ends)",
                    ("c3", 1 << 20): "profiles/r01_ncu_fused_c3.txt"}
 
 METRIC = "accepted_rk_steps_per_sec"
@@ -679,9 +679,10 @@ def _main(out):
         try:
             peak_fma = measure_fp64_peak(device)  # tera-FMA/s
             # fp64-pipe instructions (DFMA+DMUL+DADD+DSETP) per attempted sample-step of the fused
-            # Tsit5+PID Van der Pol kernel, from the ncu opcode mix (profiles/r01_ncu_fused_c2_v3.txt;
-            # 314 before the branch-free scalar path)
-            ops_per_step = 251
+            # Tsit5+PID Van der Pol kernel, from the ncu opcode mix (profiles/r01_ncu_fused_c2_v5.txt;
+            # 328 at the start of round 1, 251 with the branch-free scalar path, 210 with the
+            # table-driven pow)
+            ops_per_step = 210
             achieved = attempted_local / (kernel_ms * 1e-3) * ops_per_step / 1e12
             line["fp64_issue"] = {
                 "peak_tfma_per_s": peak_fma, "peak_source": "tode_bench_fp64_fma, measured live",
@@ -689,7 +690,8 @@ def _main(out):
                 "achieved_tinstr_per_s": achieved, "frac": achieved / peak_fma,
                 "note": "only meaningful for the fp64 workload (c2); counts the lanes that carry a sample "
                         "(a warp runs until its slowest lane is done: 92 % of the lane-steps are useful, "
-                        "the fp64 pipe itself is 73 % busy under ncu)"}
+                        "the fp64 pipe itself is 68 % busy under ncu; a warp-step costs 2 N_fp64 + N_other = "
+                        "2*210 + 234 issue cycles, the kernel runs at 96 % of that)"}
         except Exception as exc:  # measurement aid only
             line["fp64_issue"] = {"error": str(exc)}
         try:

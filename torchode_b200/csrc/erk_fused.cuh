@@ -147,6 +147,10 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) solve_fused_kernel(const 
   const CtrlP<D, T>& c = A.ctrl;
   const Field<FIELD, D, F> field(A.fp);
   const DivBy<D> div_sqrt_f((D)sqrt((double)F));
+  __shared__ __align__(16) double s_pow[kPowSharedDoubles];  // tables of det_log2 / det_exp2
+  pow_tables_to_shared(s_pow, threadIdx.x, kFusedThreads);
+  __syncthreads();
+  const PowShared pow_src{A.pow, reinterpret_cast<const double2*>(s_pow)};
 
   int ns = 0, nacc = 0, status = TODE_SUCCESS, cur = 0, fail_iter = 0x7fffffff, nonmono = 0;
   if (valid) {
@@ -220,11 +224,12 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) solve_fused_kernel(const 
 #pragma unroll
       for (int i = 1; i < S; ++i) {
         // runge_kutta.py:261-263 (FMA chain in ascending j, then addcmul)
+        const D* arow = tab.a[i];
 #pragma unroll
         for (int f = 0; f < F; ++f) {
-          D acc = mul(tab.a[i][0], k[0][f]);
+          D acc = mul(arow[0], k[0][f]);
 #pragma unroll
-          for (int j = 1; j < i; ++j) acc = ffma(tab.a[i][j], k[j][f], acc);
+          for (int j = 1; j < i; ++j) acc = ffma(arow[j], k[j][f], acc);
           y1[f] = ffma(dtD, acc, y[f]);
         }
         field(y1, k[i]);
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) solve_fused_kernel(const 
         for (int f = 0; f < F; ++f) v[f] = div_sqrt_f(q[f], ok);
         nrm = fsqrt(row_sumsq_canonical<D, F>(v));
       }
-      CtrlOut<D, T> o = controller_fast<D, T, CK>(c, nrm, dt, r1, r2, L1, L2, ok, A.pow);
+      CtrlOut<D, T> o = controller_fast<D, T, CK>(c, nrm, dt, r1, r2, L1, L2, ok, pow_src);
       if (!ok) o = error_control_checked<D, T, F>(c, err, bounds, dt, r1, r2, L1, L2);
       const bool upd = o.accept;                 // running is true inside the loop
       const T t_new = upd ? add(t, dt) : t;      // adjoints.py:151

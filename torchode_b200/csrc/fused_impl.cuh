@@ -9,10 +9,11 @@
 
 namespace tode {
 
-// resident 128-thread CTAs per SM the fused kernel is compiled for; measured on C2 / C3
-// (profiles/r01_fused_occupancy.txt): fp64 state prefers 6 (80 registers), fp32 state 4
+// resident 128-thread CTAs per SM the fused kernel is compiled for, measured on C2 / C3: fp64
+// state 5 (96 registers, ~100 B of spills; 6 = 80 registers spills ~200 B and is 4 % slower since
+// the table-driven pow, 4 and 7 are slower too), fp32 state 4
 #ifndef TODE_FUSED_MINB
-#define TODE_FUSED_MINB (sizeof(D) == 8 ? 6 : 4)
+#define TODE_FUSED_MINB (sizeof(D) == 8 ? 5 : 4)
 #endif
 
 __global__ void summary_init_kernel(int* summary);

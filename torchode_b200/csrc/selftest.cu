@@ -54,6 +54,10 @@ __device__ __forceinline__ bool same_bits(double a, double b) {
 // fast flag stayed set (so a test can tell that the fast path was actually exercised)
 __global__ void selftest_kernel(long long n, unsigned long long seed, CtrlP<double, double> c,
                                 const __grid_constant__ PowTab pt, unsigned long long* counts) {
+  __shared__ __align__(16) double s_pow[kPowSharedDoubles];
+  pow_tables_to_shared(s_pow, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const PowShared ps{pt, reinterpret_cast<const double2*>(s_pow)};
   unsigned long long bad[4] = {0, 0, 0, 0}, used[4] = {0, 0, 0, 0};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -78,14 +82,14 @@ __global__ void selftest_kernel(long long n, unsigned long long seed, CtrlP<doub
     {  // log2
       bool ok = true;
       const double x = fabs(a);
-      const double l = det_log2_fast(x, ok, pt);
+      const double l = det_log2_fast(x, ok, ps);
       if (ok) { used[1]++; if (!same_bits(l, det_log2_safe(x))) bad[1]++; }
     }
     {  // exp2 (arguments mostly in the useful range)
       const double z[3] = {mode == 1 ? a * 1e-9 : a, ldexp(gen(h2, 1), -30), gen(h3, mode)};
       double p[3];
       bool ok = true;
-      det_exp2_fast<3>(z, p, ok, pt);
+      det_exp2_fast<3>(z, p, ok, ps);
       if (ok) {
         used[2]++;
         for (int j = 0; j < 3; ++j)
@@ -103,7 +107,7 @@ __global__ void selftest_kernel(long long n, unsigned long long seed, CtrlP<doub
       cc.pid = (int)((h2 >> 20) & 1);
       if ((h2 >> 21) & 1) cc.e_prev2 = 0.0;
       bool ok = true;
-      const CtrlOut<double, double> f = controller_fast<double, double>(cc, nrm, dt, r1, r2, L1, L2, ok, pt);
+      const CtrlOut<double, double> f = controller_fast<double, double>(cc, nrm, dt, r1, r2, L1, L2, ok, ps);
       if (ok) {
         used[3]++;
         double Lr;
