@@ -509,3 +509,38 @@ def test_fast_scalar_math_is_bit_identical():
     assert got[:4] == [0, 0, 0, 0], f"mismatches (div, log2, exp2, controller): {got[:4]}"
     # the fast path must actually have been exercised: most moderate-range operands keep the flag
     assert got[4] > n // 4 and got[5] > n // 4 and got[6] > n // 8 and got[7] > n // 16, got
+
+
+@pytest.mark.parametrize("kind", ["fused", "fused_teval", "opaque"])
+def test_solve_from_host_equals_the_device_solve(kind):
+    """Chunked, stream-pipelined solve of host-resident problems: same bits as one device solve
+    (no sample fails here, so the per-chunk "failure stops the batch" scope does not show)."""
+    from torchode_b200.fields import LotkaVolterra, VanDerPol
+
+    B = 1000
+    g = torch.Generator().manual_seed(5)
+    if kind == "fused":
+        y0 = (torch.rand(B, 2, generator=g, dtype=torch.float64) * 4 - 2).pin_memory()
+        host = to.InitialValueProblem(y0, torch.zeros(B, dtype=torch.float64).pin_memory(),
+                                      torch.full((B,), 2.0, dtype=torch.float64).pin_memory())
+        term = to.ODETerm(VanDerPol(10.0))
+        solver = to.AutoDiffAdjoint(to.Tsit5(term), to.PIDController(1e-8, 1e-8, 0.2, 0.5, 0.0, term=term))
+    else:
+        y0 = (1 + torch.rand(B, 2, generator=g)).pin_memory()
+        t_eval = torch.linspace(0, 3, 17).expand(B, -1)
+        host = to.InitialValueProblem(y0, t_eval=t_eval)
+        lv = LotkaVolterra()
+        term = to.ODETerm(lv if kind == "fused_teval" else (lambda t, y: lv(t, y)))
+        solver = to.AutoDiffAdjoint(to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term))
+    dev_problem = to.InitialValueProblem(host.y0.cuda(), host.t_start.cuda(), host.t_end.cuda(),
+                                         None if host.t_eval is None else host.t_eval.cuda())
+    want = solver.solve(dev_problem)
+    got = to.solve_from_host(solver, host, "cuda", chunks=3)
+    again = to.solve_from_host(solver, host, "cuda", chunks=7, out=got)  # buffers reused
+    assert again.ys.data_ptr() == got.ys.data_ptr()
+    for sol in (got, again):
+        assert sol.ys.device.type == "cpu" and sol.ys.is_pinned()
+        assert bits_equal(sol.ys.numpy(), want.ys.cpu().numpy())
+        assert sol.status.tolist() == want.status.tolist()
+        for k in ("n_steps", "n_accepted", "n_initialized", "n_f_evals"):
+            assert sol.stats[k].tolist() == want.stats[k].tolist(), k

@@ -11,6 +11,7 @@ __version__ = "0.1.0"
 from . import fields
 from .adjoints import AutoDiffAdjoint
 from .backsolve import BacksolveAdjoint, JointBacksolveAdjoint
+from .host_pipeline import solve_from_host
 from .interface import register_method, solve_ivp
 from .problems import InitialValueProblem
 from .single_step_methods import Dopri5, Euler, Heun, Tsit5

@@ -111,9 +111,8 @@ class AutoDiffAdjoint(nn.Module):
         if problem.batch_size == 0:
             return self._empty_solution(problem, term_)
         with torch.no_grad(), torch.cuda.device(problem.device):
-            f = term_.f
-            if (isinstance(f, BuiltinField) and not term_.with_args and problem.n_features <= 4
-                    and (f.n_features is None or f.n_features == problem.n_features)):
+            f = self._fused_eligible(problem, term_)
+            if f is not None:
                 sol = self._solve_fused(problem, term_, f, dt0)
                 if sol is not None:
                     return sol
@@ -135,6 +134,19 @@ class AutoDiffAdjoint(nn.Module):
     # route 1: fused whole-solve kernel
     # ------------------------------------------------------------------------------------
     def _solve_fused(self, problem, term_, field: BuiltinField, dt0) -> Optional[Solution]:
+        return self._fused_finish(self._fused_launch(problem, term_, field, dt0))
+
+    def _fused_eligible(self, problem, term_) -> Optional[BuiltinField]:
+        """The built-in analytic field of a problem the fused whole-solve kernel covers, else None."""
+        f = term_.f
+        if (self._kernel_route() and isinstance(f, BuiltinField) and not term_.with_args
+                and problem.n_features <= 4 and (f.n_features is None or f.n_features == problem.n_features)):
+            return f
+        return None
+
+    def _fused_launch(self, problem, term_, field: BuiltinField, dt0) -> Dict[str, Any]:
+        """Allocate the outputs and enqueue the fused kernel on the current stream -- no host
+        synchronisation.  ``_fused_finish`` reads the batch summary (the one sync of the solve)."""
         lib = _cabi.lib()
         method, ctrl = self.step_method, self.step_size_controller
         dev, D, Tt = problem.device, problem.data_dtype, problem.time_dtype
@@ -168,28 +180,36 @@ class AutoDiffAdjoint(nn.Module):
         sol.ys, sol.n_steps, sol.n_accepted = ys.data_ptr(), n_steps.data_ptr(), n_accepted.data_ptr()
         sol.n_initialized, sol.status, sol.summary = n_init.data_ptr(), status.data_ptr(), summary.data_ptr()
         fp = (C.c_double * _cabi.MAX_FIELD_PARAMS)(*field.params())
-        stream = _launch.stream_ptr(dev)
 
         def run(cap: int):
             _cabi.check(lib.tode_solve_fused(field.field_id, fp, C.byref(cab_t), C.byref(cab_c),
-                                             C.byref(prob), C.byref(sol), cap, stream), "tode_solve_fused")
-            return summary.tolist()  # the one host sync of the solve (n_f_evals lives on the CPU)
+                                             C.byref(prob), C.byref(sol), cap, _launch.stream_ptr(dev)),
+                        "tode_solve_fused")
 
-        iters, first_fail, nonmono, _ = run(0)
+        run(0)
+        return dict(run=run, summary=summary, ys=ys, n_steps=n_steps, n_accepted=n_accepted, n_init=n_init,
+                    status=status, problem=problem, term=term_, n_stage_evals=cab_t.n_stages - 1,  # FSAL
+                    n_init_evals=2 if dt0 is None else 1,
+                    keep=(y0, t_start, t_end, t_eval, dt0_c))  # inputs stay alive until the kernel ran
+
+    def _fused_finish(self, ctx: Dict[str, Any], summary_host=None) -> Optional[Solution]:
+        """``summary_host``: the batch summary if the caller already copied it to the host."""
+        iters, first_fail, nonmono, _ = ctx["summary"].tolist() if summary_host is None else summary_host
         if nonmono:
             return None  # t_eval rows not monotone in time: the staged route has the general mode
         self.last_run = {"route": "fused", "kernel_launches": 2, "iterations": iters}
         if first_fail != _INT32_MAX and first_fail < iters:
             # a failure stops the WHOLE batch at that iteration (adjoints.py:186-190): replay
             # with every sample limited to the iterations the reference would have executed
-            iters, _, _, _ = run(first_fail)
+            ctx["run"](first_fail)
+            iters = ctx["summary"].tolist()[0]
             self.last_run = {"route": "fused+replay", "kernel_launches": 4, "iterations": iters}
+        problem = ctx["problem"]
         stats: Dict[str, Any] = {}
-        n_stage_evals = cab_t.n_stages - 1  # FSAL
-        _uniform_stats(term_, problem, stats, (2 if dt0 is None else 1) + n_stage_evals * iters)
-        stats["n_steps"], stats["n_accepted"], stats["n_initialized"] = n_steps, n_accepted, n_init
+        _uniform_stats(ctx["term"], problem, stats, ctx["n_init_evals"] + ctx["n_stage_evals"] * iters)
+        stats["n_steps"], stats["n_accepted"], stats["n_initialized"] = ctx["n_steps"], ctx["n_accepted"], ctx["n_init"]
         ts = problem.t_eval if problem.t_eval is not None else problem.t_end[:, None]
-        return Solution(ts=ts, ys=ys, stats=stats, status=status)
+        return Solution(ts=ts, ys=ctx["ys"], stats=stats, status=ctx["status"])
 
     # ------------------------------------------------------------------------------------
     # route 2: stage-wise kernels around an opaque f
