@@ -70,6 +70,10 @@ class AutoDiffAdjoint(nn.Module):
         # problem signature, reused by later solves (capture + instantiation cost ~10-50 ms)
         self._plans = {}
         self._rings = {}
+        # handle under which the torch.compile operator finds this solver (compile_ops.py)
+        from .compile_ops import solver_handle
+
+        self._compile_handle = solver_handle(self)
 
     def _poll_ring(self, dev, look):
         """Pinned host mirror of the control block + events, allocated once per solver and device
@@ -98,6 +102,11 @@ class AutoDiffAdjoint(nn.Module):
             term_ = term
         if not self._kernel_route():
             return self._solve_generic(problem, term, term_, dt0, args)
+        if torch.compiler.is_compiling() and term is None and args is None:
+            # inside torch.compile: one opaque operator with a fake kernel (compile_ops.py)
+            from .compile_ops import solve_compiled
+
+            return solve_compiled(self, problem, dt0)
 
         _launch.require_cuda(problem.y0, problem.t_start, problem.t_end, problem.t_eval, dt0)
         if torch.is_grad_enabled() and (
