@@ -372,11 +372,23 @@ def cpu_cores():
         return os.cpu_count() or 1
 
 
+def cpu_threads():
+    """OpenMP threads the oracle port runs with: all host cores this process may use (torchrun
+    exports OMP_NUM_THREADS=1, which would make the CPU arm look 10-20x slower than it is)."""
+    from oracle import oracle as orc
+
+    lib = orc.lib()
+    lib.orc_set_threads.restype = C.c_int
+    lib.orc_set_threads.argtypes = [C.c_int]
+    return int(lib.orc_set_threads(cpu_cores()))
+
+
 def run_reference_arm(args, workload, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     sb = cpu_sample_size(workload)
+    threads = cpu_threads()
     values, times = [], []
     for i in range(args.warmup + args.steps):
         v, t, _ = cpu_run(workload, sb)
@@ -391,7 +403,7 @@ def run_reference_arm(args, workload, out):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": workload.dtype_name,
         "data": "synthetic", "config": {"workload": workload.describe(), "batch_per_step": sb},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_cores(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -540,7 +552,7 @@ def _main(out):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
-    from torchode_b200.distributed import gather_solution
+    from torchode_b200.distributed import SymmetricWorkspace, gather_solution, solve_sharded_symmetric
 
     hbm_peak, peak_src = peaks()
     B = workload.batch
@@ -556,7 +568,21 @@ def _main(out):
     solver.use_cuda_graph = getattr(workload, "graph", False)
     l2buf = torch.zeros(128 << 20, dtype=torch.float32, device=device)  # 512 MiB
 
+    # N > 1, fused route: the kernel writes the gathered Solution into every rank's symmetric
+    # (peer-mapped) buffers while it solves -- no all-gather after the solve; stage-wise workloads
+    # gather with NCCL
+    ws, ts_full = None, None
+    if world > 1 and not getattr(workload, "staged", False):
+        ws = SymmetricWorkspace(B, T, int(problem.n_features), problem.data_dtype, device)
+        if T == 0:
+            ts_full = problem.t_end.new_empty((B * world, 1))
+            dist.all_gather_into_tensor(ts_full, problem.t_end[:, None].contiguous())
+        else:
+            ts_full = problem.t_eval[:1].expand(B * world, -1)  # the workloads share one t_eval row
+
     def step():
+        if ws is not None:
+            return solve_sharded_symmetric(solver, problem, ws, ts=ts_full)
         sol = solver.solve(problem)
         if world > 1:
             sol = gather_solution(sol, B * world, ts=None if T == 0 else problem.t_eval)
@@ -685,7 +711,11 @@ def _main(out):
                    "l2": "512 MiB buffer rewritten between timed steps (L2 flush)",
                    "loop_iterations": iters, "mean_n_steps": mean_steps,
                    "samples_with_failure_status": n_status,
-                   "multi_gpu": "independent batch slices, NCCL all-gather of ys/stats after the solve"},
+                   "multi_gpu": ("independent batch slices; the fused kernel stores every result into all ranks' "
+                                 "symmetric (NVLink peer-mapped) gathered buffers and publishes its iteration count "
+                                 "with system-scope atomics, two signal-pad barriers per step, no collective"
+                                 if ws is not None else
+                                 "independent batch slices, NCCL all-gather of ys/stats after the solve")},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(e2e_s[0]) * 1e3,
@@ -725,9 +755,10 @@ def _main(out):
             line["roofline_kernels"] = {"error": str(exc)}
         try:
             sb = cpu_sample_size(workload)
+            threads = cpu_threads()
             v, t, _ = cpu_run(workload, sb)
             line["cpu_baseline"] = {
-                "value": v, "unit": UNIT, "cores": cpu_cores(), "kind": "port",
+                "value": v, "unit": UNIT, "cores": threads, "kind": "port",
                 "sample": f"{sb} of {B} samples of the same seeded workload, oracle port (plain C + OpenMP), "
                           f"{t:.1f} s"}
         except Exception as exc:

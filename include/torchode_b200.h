@@ -40,9 +40,10 @@
 extern "C" {
 #endif
 
-#define TODE_ABI_VERSION 1
+#define TODE_ABI_VERSION 2
 #define TODE_MAX_STAGES 7
 #define TODE_MAX_FIELD_PARAMS 8
+#define TODE_MAX_PEERS 8
 
 /* argument-error codes (negative; CUDA errors are returned as positive values) */
 #define TODE_EINVAL (-1)   /* bad argument (NULL pointer, bad size, bad enum)    */
@@ -193,6 +194,26 @@ typedef struct tode_solution {
    * reference), [1] first iteration (1-based) at which any sample reported a
    * status != SUCCESS or INT32_MAX, [2] non-monotone t_eval flag */
   int32_t* summary;
+  /* Multi-GPU, "write the all-gather while solving" (replaces the all_gather of ys / statistics
+   * that follows a sharded solve): with n_peers > 0 every result of sample b --
+   * its ys rows as they are produced and its statistics when it finishes -- is ALSO stored at
+   * row peer_row0 + b of the gathered buffers of n_peers replicas.  The pointers must be valid
+   * on THIS GPU (peer memory mapped over NVLink, e.g. one symmetric-memory allocation per rank;
+   * a replica may be this GPU's own gathered buffer).  peer_global[p] = device int32[4] of
+   * replica p, zeroed before the launch on every rank: after the solve kernel a one-warp
+   * epilogue kernel either atomicMax-es this shard's iteration count into [0] of every
+   * replica, or -- if this shard needs the failure replay (summary[1] < summary[0]) -- ORs 1
+   * into [1] and leaves [0] alone until the replay (iter_cap > 0) has run.  No collective, no
+   * host synchronisation; the caller brackets the launch with two cross-GPU barriers. */
+  int32_t n_peers;
+  int32_t reserved;
+  int64_t peer_row0;
+  void* peer_ys[TODE_MAX_PEERS];
+  int64_t* peer_n_steps[TODE_MAX_PEERS];
+  int64_t* peer_n_accepted[TODE_MAX_PEERS];
+  int64_t* peer_n_initialized[TODE_MAX_PEERS];
+  int64_t* peer_status[TODE_MAX_PEERS];
+  int32_t* peer_global[TODE_MAX_PEERS];
 } tode_solution;
 
 int tode_abi_version(void);

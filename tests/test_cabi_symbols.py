@@ -33,7 +33,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_cabi.Controller) == 16 + 8 * 11 + 8
     assert ctypes.sizeof(_cabi.State) == 3 * 8 + 8 + 3 * 8 + 8 + 16 * 8 + 8
     assert ctypes.sizeof(_cabi.Problem) == 3 * 8 + 8 + 4 * 8 + 8 + 8
-    assert ctypes.sizeof(_cabi.SolutionOut) == 8 * 8
+    assert ctypes.sizeof(_cabi.SolutionOut) == 8 * 8 + 8 + 8 + 6 * 8 * _cabi.MAX_PEERS  # + peer replicas (ABI 2)
 
 
 def test_argument_errors_are_reported_not_thrown():

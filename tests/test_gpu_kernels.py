@@ -544,3 +544,49 @@ def test_solve_from_host_equals_the_device_solve(kind):
         assert sol.status.tolist() == want.status.tolist()
         for k in ("n_steps", "n_accepted", "n_initialized", "n_f_evals"):
             assert sol.stats[k].tolist() == want.stats[k].tolist(), k
+
+
+@pytest.mark.parametrize("with_t_eval", [False, True])
+def test_fused_kernel_writes_replicas_of_the_gathered_buffers(with_t_eval):
+    """tode_solution.peer_*: the multi-GPU "write the all-gather while solving" path, exercised on
+    one GPU with two replicas that both live here (on a box they are peer mappings over NVLink)."""
+    from torchode_b200.fields import LotkaVolterra
+
+    B, F, T, world, rank = 300, 2, 9, 2, 1
+    g = torch.Generator().manual_seed(11)
+    y0 = (1 + torch.rand(B, F, generator=g)).cuda()
+    t_eval = torch.linspace(0, 2, T).cuda().expand(B, -1) if with_t_eval else None
+    prob = to.InitialValueProblem(y0, torch.zeros(B, device="cuda"), torch.full((B,), 2.0, device="cuda"), t_eval)
+    term = to.ODETerm(LotkaVolterra())
+    solver = to.AutoDiffAdjoint(to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term))
+    want = solver.solve(prob)
+    Tn = T if with_t_eval else 1
+
+    class Replicas:  # stands in for distributed.SymmetricWorkspace
+        def __init__(self):
+            G = world * B
+            self.ys = [torch.full((G, Tn, F), -7.0, device="cuda") for _ in range(world)]
+            self.stats = [torch.full((4, G), -7, dtype=torch.long, device="cuda") for _ in range(world)]
+            self.glob = [torch.zeros(4, dtype=torch.int32, device="cuda") for _ in range(world)]
+
+        def fill(self, sol, b, n_points, f, dtype):
+            sol.n_peers, sol.peer_row0 = world, rank * B
+            for p in range(world):
+                sol.peer_ys[p] = self.ys[p].data_ptr()
+                for k, name in enumerate(("peer_n_steps", "peer_n_accepted", "peer_n_initialized", "peer_status")):
+                    getattr(sol, name)[p] = self.stats[p][k].data_ptr()
+                sol.peer_global[p] = self.glob[p].data_ptr()
+
+    reps = Replicas()
+    ctx = solver._fused_launch(prob, term, term.f, None, peers=reps)
+    got = solver._fused_finish(ctx)
+    assert bits_equal(got.ys.cpu().numpy(), want.ys.cpu().numpy())
+    iters = (int(want.stats["n_f_evals"][0]) - 2) // 6
+    lo, hi = rank * B, (rank + 1) * B
+    for p in range(world):
+        assert bits_equal(reps.ys[p][lo:hi].cpu().numpy(), want.ys.cpu().numpy())
+        assert bool((reps.ys[p][:lo] == -7).all())  # other shards' rows untouched
+        for k, ref in enumerate((want.stats["n_steps"], want.stats["n_accepted"], want.stats["n_initialized"],
+                                 want.status)):
+            assert reps.stats[p][k][lo:hi].tolist() == ref.tolist()
+        assert reps.glob[p].tolist() == [iters, 0, 0, 0]

@@ -7,9 +7,10 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_STAGES = 7
 MAX_FIELD_PARAMS = 8
+MAX_PEERS = 8
 
 # enum tode_dtype
 F32, F64 = 0, 1
@@ -120,6 +121,15 @@ class SolutionOut(C.Structure):
         ("t_final", _vp),
         ("dt_final", _vp),
         ("summary", _vp),
+        ("n_peers", C.c_int32),
+        ("reserved", C.c_int32),
+        ("peer_row0", C.c_int64),
+        ("peer_ys", _vp * MAX_PEERS),
+        ("peer_n_steps", _vp * MAX_PEERS),
+        ("peer_n_accepted", _vp * MAX_PEERS),
+        ("peer_n_initialized", _vp * MAX_PEERS),
+        ("peer_status", _vp * MAX_PEERS),
+        ("peer_global", _vp * MAX_PEERS),
     ]
 
 

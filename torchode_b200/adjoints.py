@@ -153,9 +153,13 @@ class AutoDiffAdjoint(nn.Module):
             return f
         return None
 
-    def _fused_launch(self, problem, term_, field: BuiltinField, dt0) -> Dict[str, Any]:
+    def _fused_launch(self, problem, term_, field: BuiltinField, dt0, peers=None) -> Dict[str, Any]:
         """Allocate the outputs and enqueue the fused kernel on the current stream -- no host
-        synchronisation.  ``_fused_finish`` reads the batch summary (the one sync of the solve)."""
+        synchronisation.  ``_fused_finish`` reads the batch summary (the one sync of the solve).
+
+        ``peers``: a ``distributed.SymmetricWorkspace`` -- the kernel then also stores every result
+        into each rank's gathered buffers (peer memory over NVLink) and publishes the iteration
+        count to every rank (``tode_solution.peer_*``)."""
         lib = _cabi.lib()
         method, ctrl = self.step_method, self.step_size_controller
         dev, D, Tt = problem.device, problem.data_dtype, problem.time_dtype
@@ -189,6 +193,8 @@ class AutoDiffAdjoint(nn.Module):
         sol.ys, sol.n_steps, sol.n_accepted = ys.data_ptr(), n_steps.data_ptr(), n_accepted.data_ptr()
         sol.n_initialized, sol.status, sol.summary = n_init.data_ptr(), status.data_ptr(), summary.data_ptr()
         fp = (C.c_double * _cabi.MAX_FIELD_PARAMS)(*field.params())
+        if peers is not None:
+            peers.fill(sol, B, max(Tn, 1), F, D)
 
         def run(cap: int):
             _cabi.check(lib.tode_solve_fused(field.field_id, fp, C.byref(cab_t), C.byref(cab_c),

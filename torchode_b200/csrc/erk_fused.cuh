@@ -96,6 +96,14 @@ struct FusedArgs {
   int* summary;
   long long iter_cap;  // <= 0: unlimited
   double e_init;       // 1/order pre-rounded to D
+  // replicas of the gathered result buffers (tode_solution.peer_*): row peer_row0 + b of each
+  int n_peers;
+  long long peer_row0;
+  D* p_ys[TODE_MAX_PEERS];
+  long long* p_n_steps[TODE_MAX_PEERS];
+  long long* p_n_accepted[TODE_MAX_PEERS];
+  long long* p_n_initialized[TODE_MAX_PEERS];
+  long long* p_status[TODE_MAX_PEERS];
 };
 
 template <typename D, int F>
@@ -160,7 +168,13 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) solve_fused_kernel(const 
     const T dir = dir_of(ts, te);
     const T t_min = ts < te ? ts : te, t_max = ts < te ? te : ts;
     const T* tev = Tn > 0 ? A.t_eval + b * A.te_stride : nullptr;
-    D* ye = A.ys + b * (Tn > 0 ? Tn : 1) * F;
+    const long long row_elems = (Tn > 0 ? Tn : 1) * F;
+    D* ye = A.ys + b * row_elems;
+    // result row `idx` of this sample: here and into every replica of the gathered buffers
+    auto put_row = [&](long long idx, const D* r) {
+      store_row<D, F>(ye + idx * F, r);
+      for (int p = 0; p < A.n_peers; ++p) store_row<D, F>(A.p_ys[p] + (A.peer_row0 + b) * row_elems + idx * F, r);
+    };
     T t = ts, dt;
     field(y, k[0]);  // controller.init / ExplicitRungeKutta.init: f0 = f(t_start, y0)
 
@@ -202,13 +216,13 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) solve_fused_kernel(const 
     // ---- evaluation exactly at t_start, monotonicity of the t_eval row -------------------
     if (Tn > 0) {
       if (tev[0] == ts) {  // adjoints.py:123-126
-        store_row<D, F>(ye, y);
+        put_row(0, y);
         cur = 1;
       }
       for (long long j = 1; j < Tn; ++j)
         if (mul(dir, tev[j]) < mul(dir, tev[j - 1])) nonmono = 1;
     } else {
-      store_row<D, F>(ye, y);  // never hand out uninitialised memory
+      put_row(0, y);  // never hand out uninitialised memory
     }
 
     D r1 = (D)1, r2 = (D)1;
@@ -273,7 +287,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) solve_fused_kernel(const 
       // ---- dense output (adjoints.py:215-234, 298-301) ------------------------------------
       bool have_co = false;
       D co[F][5];
-      auto eval_at = [&](T tq, D* dst) {
+      auto eval_at = [&](T tq, long long idx) {
         if (!have_co) {
 #pragma unroll
           for (int f = 0; f < F; ++f) {
@@ -288,18 +302,18 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) solve_fused_kernel(const 
         D out[F];
 #pragma unroll
         for (int f = 0; f < F; ++f) out[f] = horner4<D>(co[f], x);
-        store_row<D, F>(dst, out);
+        put_row(idx, out);
       };
       if (Tn == 0) {
         // the interpolant of the sample's LAST loop iteration, evaluated at t_end: the
         // iteration in which it finishes, fails, or the batch is cut off (iter_cap)
         if (!running_new || status != TODE_SUCCESS || ns >= iter_cap)
-          eval_at(te, ye);
+          eval_at(te, 0);
       } else {
         while (cur < Tn) {
           const T tq = tev[cur];
           if (!(ffma(dir, t_new, mul(-dir, tq)) >= (T)0)) break;
-          eval_at(tq, ye + (long long)cur * F);
+          eval_at(tq, cur);
           ++cur;
         }
       }
@@ -331,6 +345,13 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) solve_fused_kernel(const 
     A.n_accepted[b] = nacc;
     A.n_initialized[b] = Tn > 0 ? cur : 1;
     A.status[b] = status;
+    for (int p = 0; p < A.n_peers; ++p) {
+      const long long g = A.peer_row0 + b;
+      A.p_n_steps[p][g] = ns;
+      A.p_n_accepted[p][g] = nacc;
+      A.p_n_initialized[p][g] = Tn > 0 ? cur : 1;
+      A.p_status[p][g] = status;
+    }
     if (A.t_final != nullptr) A.t_final[b] = t;
     if (A.dt_final != nullptr) A.dt_final[b] = dt;
   }

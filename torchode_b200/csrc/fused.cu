@@ -13,6 +13,24 @@ __global__ void summary_init_kernel(int* summary) {
   summary[3] = 0;
 }
 
+// Multi-GPU epilogue (tode_solution.peer_global): one thread publishes this shard's iteration count
+// -- or its need for the failure replay -- to every replica with system-scope atomics.
+struct PeerGlobals {
+  int n;
+  int* g[TODE_MAX_PEERS];
+};
+__global__ void peer_epilogue_kernel(const int* summary, PeerGlobals pg, int after_replay) {
+  const int iters = summary[0], first_fail = summary[1];
+  const bool need_replay = !after_replay && first_fail != INT_MAX && first_fail < iters;
+  for (int p = 0; p < pg.n; ++p) {
+    if (need_replay)
+      atomicOr_system(pg.g[p] + 1, 1);
+    else
+      atomicMax_system(pg.g[p] + 0, iters);
+  }
+  __threadfence_system();
+}
+
 // fused_impl.cuh, instantiated in fused_f32f32.cu / fused_f64f64.cu / fused_f32f64.cu / fused_f64f32.cu
 template <typename D, typename T>
 int launch_fused(int field, const double* fp, const tode_tableau* tab, const tode_controller* ctrl,
@@ -30,6 +48,12 @@ extern "C" int tode_solve_fused(int field, const double* field_params, const tod
   if (!sol->ys || !sol->n_steps || !sol->n_accepted || !sol->n_initialized || !sol->status || !sol->summary)
     return TODE_EINVAL;
 #define CALL(D, T) launch_fused<D, T>(field, field_params, tab, ctrl, prob, sol, iter_cap, static_cast<cudaStream_t>(stream))
-  TODE_DISPATCH_DT(prob->data_dtype, prob->time_dtype, CALL);
+  const int rc = [&]() -> int { TODE_DISPATCH_DT(prob->data_dtype, prob->time_dtype, CALL); }();
 #undef CALL
+  if (rc != 0 || sol->n_peers <= 0 || prob->B == 0) return rc;
+  PeerGlobals pg{};
+  pg.n = sol->n_peers;
+  for (int p = 0; p < sol->n_peers; ++p) pg.g[p] = sol->peer_global[p];
+  peer_epilogue_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(sol->summary, pg, iter_cap > 0 ? 1 : 0);
+  return launch_status();
 }

@@ -75,6 +75,20 @@ int launch_fused(int field, const double* fp, const tode_tableau* tab, const tod
   a.summary = sol->summary;
   a.iter_cap = iter_cap;
   a.e_init = round_exp<D>(1.0 / (double)tab->order);
+  if (sol->n_peers < 0 || sol->n_peers > TODE_MAX_PEERS) return TODE_EINVAL;
+  a.n_peers = sol->n_peers;
+  a.peer_row0 = sol->peer_row0;
+  for (int p = 0; p < sol->n_peers; ++p) {
+    if (!sol->peer_ys[p] || !sol->peer_n_steps[p] || !sol->peer_n_accepted[p] || !sol->peer_n_initialized[p] ||
+        !sol->peer_status[p] || !sol->peer_global[p])
+      return TODE_EINVAL;
+    if (!aligned_to(sol->peer_ys[p], al)) return TODE_EALIGN;
+    a.p_ys[p] = static_cast<D*>(sol->peer_ys[p]);
+    a.p_n_steps[p] = reinterpret_cast<long long*>(sol->peer_n_steps[p]);
+    a.p_n_accepted[p] = reinterpret_cast<long long*>(sol->peer_n_accepted[p]);
+    a.p_n_initialized[p] = reinterpret_cast<long long*>(sol->peer_n_initialized[p]);
+    a.p_status[p] = reinterpret_cast<long long*>(sol->peer_status[p]);
+  }
   if (a.B == 0) return 0;
   // what the controller needs: 0 = no history, 1 = r1 only, 2 = r1 and r2
   const int ck = !a.ctrl.pid ? 0 : (a.ctrl.e_prev2 == 0.0 ? 1 : 2);

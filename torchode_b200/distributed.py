@@ -91,15 +91,128 @@ def gather_solution(local: Solution, global_batch: int, ts: Optional[torch.Tenso
     return Solution(ts=ts, ys=ys, stats=stats, status=status)
 
 
+class SymmetricWorkspace:
+    """Gathered result buffers of a sharded fused solve in symmetric (peer-mapped) memory.
+
+    One ``torch.distributed._symmetric_memory`` allocation per rank holds the gathered ``ys``, the
+    four gathered int64 statistics and a 4-word global block; every rank maps every other rank's
+    allocation over NVLink.  The fused solve kernel of rank r writes the results of its samples
+    into rows ``[r * B_local, (r + 1) * B_local)`` of EVERY rank's buffers while it solves and
+    publishes its iteration count with system-scope atomics: the all-gather that used to follow the
+    solve is gone -- what is left between the ranks is two barriers around the launch (signal
+    pads of the symmetric allocation, stream-ordered, no host sync).
+
+    Equal shard sizes, one node (<= 8 ranks), built-in analytic fields (the fused route) only; the
+    returned Solution aliases the workspace -- it is overwritten by the next solve that uses it."""
+
+    MAX_PEERS = 8
+
+    def __init__(self, local_batch: int, n_points: int, n_features: int, dtype: torch.dtype, device,
+                 group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        assert self.world <= self.MAX_PEERS, "one node: at most 8 ranks"
+        self.local_batch, self.n_points, self.n_features, self.dtype = local_batch, max(n_points, 1), n_features, dtype
+        G = self.world * local_batch
+        esz = torch.empty((), dtype=dtype).element_size()
+
+        def up(n):
+            return (n + 255) // 256 * 256
+
+        self._off_ys = 0
+        self._off_stats = up(G * self.n_points * n_features * esz)
+        self._off_global = self._off_stats + up(4 * G * 8)
+        total = self._off_global + 256
+        self.buf = symm.empty(total, dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.buf.zero_()
+        self.ys = self.buf[self._off_ys: self._off_ys + G * self.n_points * n_features * esz].view(dtype).view(
+            G, self.n_points, n_features)
+        stats = self.buf[self._off_stats: self._off_stats + 4 * G * 8].view(torch.long).view(4, G)
+        self.n_steps, self.n_accepted, self.n_initialized, self.status = stats[0], stats[1], stats[2], stats[3]
+        self.glob = self.buf[self._off_global: self._off_global + 16].view(torch.int32)
+        self.bases = [int(p) for p in self.hdl.buffer_ptrs]
+        self.barrier()
+
+    def matches(self, local_batch, n_points, n_features, dtype) -> bool:
+        return (self.local_batch, self.n_points, self.n_features, self.dtype) == (
+            local_batch, max(n_points, 1), n_features, dtype)
+
+    def barrier(self):
+        """Cross-GPU barrier on the current stream (signal pads of the symmetric allocation)."""
+        self.hdl.barrier()
+
+    def fill(self, sol, B, n_points, F, dtype):
+        """Set the peer_* fields of a ``tode_solution`` (called by ``AutoDiffAdjoint._fused_launch``)."""
+        assert self.matches(B, n_points, F, dtype), "workspace was built for another problem shape"
+        G = self.world * self.local_batch
+        sol.n_peers, sol.peer_row0 = self.world, self.rank * self.local_batch
+        for p, base in enumerate(self.bases):
+            sol.peer_ys[p] = base + self._off_ys
+            for k, name in enumerate(("peer_n_steps", "peer_n_accepted", "peer_n_initialized", "peer_status")):
+                getattr(sol, name)[p] = base + self._off_stats + k * G * 8
+            sol.peer_global[p] = base + self._off_global
+
+
+def solve_sharded_symmetric(solver, local_problem: InitialValueProblem, ws: SymmetricWorkspace, *,
+                            dt0: Optional[torch.Tensor] = None, ts: Optional[torch.Tensor] = None) -> Solution:
+    """Solve this rank's shard with the fused kernel writing straight into every rank's gathered
+    buffers (``ws``); returns the full-batch Solution (aliasing ``ws``).  Collective: every rank
+    of the group must call it.  ``ts``: the full-batch evaluation times if the caller has them
+    (else this rank's ``ts`` is gathered with NCCL)."""
+    from .adjoints import _INT32_MAX
+
+    term_ = solver.step_method.term
+    field = solver._fused_eligible(local_problem, term_) if term_ is not None else None
+    if field is None:
+        raise NotImplementedError("solve_sharded_symmetric needs a built-in analytic field (the fused route); "
+                                  "use solve_sharded for opaque vector fields")
+    with torch.no_grad(), torch.cuda.device(local_problem.device):
+        ws.glob.zero_()
+        ws.barrier()  # every rank has reset its global block and is done with the previous results
+        ctx = solver._fused_launch(local_problem, term_, field, dt0, peers=ws)
+        ws.barrier()  # every rank's kernel (and its peer stores / atomics) has completed
+        g_iters, g_replay, _, _ = ws.glob.tolist()  # the one host sync
+        if g_replay:
+            # some shard saw a failure before its last iteration: "any failure stops the batch"
+            # holds per shard -- that shard replays with the cap and republishes
+            iters, first_fail, _, _ = ctx["summary"].tolist()
+            if first_fail != _INT32_MAX and first_fail < iters:
+                ctx["run"](first_fail)
+            ws.barrier()
+            g_iters = ws.glob.tolist()[0]
+        if ctx["summary"].tolist()[2]:
+            raise NotImplementedError("non-monotone t_eval rows need the stage-wise route: use solve_sharded")
+    G = ws.world * ws.local_batch
+    stats = {"n_steps": ws.n_steps, "n_accepted": ws.n_accepted, "n_initialized": ws.n_initialized}
+    if getattr(term_, "with_stats", True):
+        stats["n_f_evals"] = torch.full((1,), ctx["n_init_evals"] + ctx["n_stage_evals"] * g_iters,
+                                        dtype=torch.long).expand(G)
+    if ts is None:
+        sizes = [ws.local_batch] * ws.world
+        lts = local_problem.t_eval if local_problem.t_eval is not None else local_problem.t_end[:, None]
+        ts = _gather_rows(lts, sizes, ws.group)
+    solver.last_run = {"route": "fused+peer-stores", "kernel_launches": 3, "iterations": g_iters}
+    return Solution(ts=ts, ys=ws.ys, stats=stats, status=ws.status)
+
+
 def solve_sharded(solver, problem: InitialValueProblem, *, dt0: Optional[torch.Tensor] = None,
-                  args=None, group=None, gather: bool = True) -> Solution:
+                  args=None, group=None, gather: bool = True,
+                  workspace: Optional[SymmetricWorkspace] = None) -> Solution:
     """Every rank holds (or can build) the full problem; each solves its slice.
 
-    With ``gather=False`` the local Solution is returned (statistics of the slice only)."""
+    With ``gather=False`` the local Solution is returned (statistics of the slice only).  With a
+    ``workspace`` (equal slices, built-in field) the fused kernel writes the gathered Solution
+    itself (``solve_sharded_symmetric``) instead of the NCCL all-gathers."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     lo, hi = shard_bounds(problem.batch_size, rank, world)
-    local = solver.solve(shard_problem(problem, rank, world),
-                         dt0=None if dt0 is None else dt0[lo:hi], args=args)
+    local_problem = shard_problem(problem, rank, world)
+    dt0_local = None if dt0 is None else dt0[lo:hi]
+    if workspace is not None and gather:
+        return solve_sharded_symmetric(solver, local_problem, workspace, dt0=dt0_local, ts=problem.t_eval)
+    local = solver.solve(local_problem, dt0=dt0_local, args=args)
     if not gather:
         return local
     return gather_solution(local, problem.batch_size, ts=problem.t_eval, group=group)
