@@ -727,6 +727,7 @@ def _main(out):
         "gpu_launches": int(last_run.get("kernel_launches", last_run.get("kernel_launches_min", 0))) * args.steps,
         "route": last_run,
         "wall_s_timed_region": t_wall,
+        "step_ms_rank0": [round(t, 4) for t in times],
     }
     if clocks is not None:
         line["clocks"] = clocks
