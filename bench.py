@@ -573,7 +573,17 @@ def _main(out):
     # gather with NCCL
     ws, ts_full = None, None
     if world > 1 and not getattr(workload, "staged", False):
-        ws = SymmetricWorkspace(B, T, int(problem.n_features), problem.data_dtype, device)
+        try:
+            ws = SymmetricWorkspace(B, T, int(problem.n_features), problem.data_dtype, device)
+        except Exception as exc:  # no symmetric memory on this box: every rank falls back to NCCL
+            print(f"[rank {rank}] symmetric memory unavailable ({type(exc).__name__}: {exc}); NCCL gather",
+                  file=sys.stderr)
+            ws = None
+        ok = torch.tensor([1 if ws is not None else 0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not int(ok):
+            ws = None
+    if ws is not None:
         if T == 0:
             ts_full = problem.t_end.new_empty((B * world, 1))
             dist.all_gather_into_tensor(ts_full, problem.t_end[:, None].contiguous())
