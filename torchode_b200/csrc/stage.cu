@@ -5,10 +5,23 @@
 
 namespace tode {
 
+// vectors per thread: keep >= ~96 bytes of loads in flight per thread (early stages read few rows
+// and narrow rows give narrow vectors: with 2 vectors per thread NK = 1, 2 on 8-byte rows reached
+// only 78 % / 83 % of the copy bandwidth, profiles/r01_bench_c2.json roofline_kernels)
+#ifndef TODE_STAGE_BYTES_IN_FLIGHT
+#define TODE_STAGE_BYTES_IN_FLIGHT 96
+#endif
+template <typename D, int VEC, int NK>
+constexpr int stage_unroll() {
+  const int per_vec = (NK + 1) * VEC * (int)sizeof(D);
+  const int u = (TODE_STAGE_BYTES_IN_FLIGHT + per_vec - 1) / per_vec;
+  return u < 2 ? 2 : (u > 8 ? 8 : u);
+}
+
 template <typename D, typename T, int VEC, int NK>
 static int launch_stage_nk(const tode_tableau* tab, int stage, const tode_state* st,
                            const void* const* k, void* y_out, cudaStream_t stream) {
-  constexpr int UNROLL = 2;
+  constexpr int UNROLL = stage_unroll<D, VEC, NK>();
   StageArgs<D, T, NK> a{};
   for (int j = 0; j < NK; ++j) {
     a.a[j] = (D)tab->a[stage][j];
