@@ -590,3 +590,38 @@ def test_fused_kernel_writes_replicas_of_the_gathered_buffers(with_t_eval):
                                  want.status)):
             assert reps.stats[p][k][lo:hi].tolist() == ref.tolist()
         assert reps.glob[p].tolist() == [iters, 0, 0, 0]
+
+
+def test_solve_from_host_edge_cases():
+    """Chunks are independent solves: a failing sample stops its own chunk only (the documented
+    per-chunk scope), non-monotone t_eval rows fall back to the stage-wise route inside their chunk,
+    user dt0 and an empty batch pass through."""
+    from torchode_b200.fields import LotkaVolterra
+
+    B, chunks = 96, 3
+    g = torch.Generator().manual_seed(21)
+    y0 = 1 + torch.rand(B, 2, generator=g)
+    y0[70, 0] = float("inf")  # third chunk (rows 64..95) fails at its first step
+    t_eval = torch.linspace(0, 3, 11).repeat(B, 1)
+    t_eval[5] = t_eval[5].flip(0) * 0 + torch.tensor([0, 2, 1, 3, 4, 5, 6, 7, 8, 9, 10.0]) * 0.3  # row 5 not monotone
+    dt0 = torch.full((B,), 1e-3)
+    term = to.ODETerm(LotkaVolterra())
+    solver = to.AutoDiffAdjoint(to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term))
+    host = to.InitialValueProblem(y0.pin_memory(), t_eval=t_eval.pin_memory())
+    got = to.solve_from_host(solver, host, "cuda", chunks=chunks, dt0=dt0)
+    n_f = 0
+    for c in range(chunks):
+        lo, hi = c * 32, (c + 1) * 32
+        want = solver.solve(to.InitialValueProblem(y0[lo:hi].cuda(), t_eval=t_eval[lo:hi].cuda()), dt0=dt0[lo:hi].cuda())
+        n_init = want.stats["n_initialized"].cpu()
+        for b in range(32):  # only initialised evaluation points are defined
+            k = int(n_init[b])
+            assert bits_equal(got.ys[lo + b, :k].numpy(), want.ys[b, :k].cpu().numpy()), (c, b)
+        assert got.status[lo:hi].tolist() == want.status.tolist()
+        for key in ("n_steps", "n_accepted", "n_initialized"):
+            assert got.stats[key][lo:hi].tolist() == want.stats[key].tolist(), (c, key)
+        n_f = max(n_f, int(want.stats["n_f_evals"][0]))
+    assert int(got.stats["n_f_evals"][0]) == n_f
+    assert int(got.status[70]) != 0 and int((got.status[:64] != 0).sum()) == 0
+    empty = to.solve_from_host(solver, to.InitialValueProblem(torch.empty(0, 2), t_eval=torch.empty(0, 11)), "cuda")
+    assert empty.ys.shape == (0, 11, 2) and empty.status.shape == (0,)
