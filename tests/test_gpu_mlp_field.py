@@ -30,7 +30,7 @@ def make_field(n_layers=3, gain=3.0, seed=1234):
     return TanhMLP256.from_sequential(seq).to(DEV)
 
 
-@pytest.mark.parametrize("B", [1, 37, 128, 129, 1000, 8192])
+@pytest.mark.parametrize("B", [1, 37, 64, 65, 128, 129, 1000, 8192, 19000])  # < 148 x 128 rows: 64-row tiles, else 128-row tiles
 @pytest.mark.parametrize("n_layers", [1, 2, 3])
 def test_kernel_matches_fp32_reference(B, n_layers):
     field = make_field(n_layers)

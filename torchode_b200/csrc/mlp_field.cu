@@ -4,10 +4,19 @@
 // issued by one elected thread), bias + tanh epilogue out of TMEM (tcgen05.ld), the activation
 // tile of a CTA never leaves shared memory between layers.
 //
-// One CTA = 128 rows of the batch (UMMA M = 128, N = 256, K = 16 per instruction, 16 per layer).
-// Shared memory holds the activation tile (128 x 256 bf16, 64 KB) and one layer's weights
-// (256 x 256 bf16, 128 KB), both K-major in the canonical SWIZZLE_128B layout: K-blocks of 64
-// elements (128 B rows), 8-row atoms of 1024 B (SBO), 16-byte chunks XOR-swizzled with row % 8.
+// One CTA = BM rows of the batch (UMMA M = BM, N = 256, K = 16 per instruction, 16 per layer).
+// Shared memory holds the activation tile (BM x 256 bf16) and one layer's weights (256 x 256
+// bf16, 128 KB), both K-major in the canonical SWIZZLE_128B layout: K-blocks of 64 elements
+// (128 B rows), 8-row atoms of 1024 B (SBO), 16-byte chunks XOR-swizzled with row % 8.
+//
+// BM = 128 for large batches; BM = 64 when 128-row tiles would leave SMs idle (B = 8192 of
+// configs[3]: 64 CTAs on 148 SMs).  An M = 64 UMMA costs the tensor core as much as M = 128, but the
+// epilogue -- bound by MUFU.TANH, 16 lanes / clk / SM, 51 % of the kernel at BM = 128 (phase
+// stamps of -DTODE_MLP_TIMING) -- and the tile loads halve per CTA while twice as many SMs work.
+// M = 64 accumulators occupy lanes 0..15 of each TMEM subpartition (row r -> lane 32 (r / 16) +
+// r % 16, probed with scripts/probes/umma_m64_layout.cu); they are read with tcgen05.ld.16x256b,
+// which spreads 16 lanes over all 32 threads in the mma C-fragment layout (thread l, repeat j:
+// rows l / 4 and l / 4 + 8, columns 8 j + 2 (l % 4) + {0, 1}; scripts/probes/umma_m64_ld16x256b.cu).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,16 +27,15 @@ namespace tode {
 namespace mlp {
 
 constexpr int kWidth = 256;
-constexpr int kBM = 128;                       // rows per CTA (UMMA M)
 constexpr int kThreads = 512;                  // 16 warps: 4 TMEM lane quarters x 4 column quarters
 constexpr int kKBlock = 64;                    // bf16 elements per 128-byte swizzle row
 constexpr int kNumKBlocks = kWidth / kKBlock;  // 4
-constexpr int kABlockBytes = kBM * 128;        // 16 KB per K-block of the activation tile
 constexpr int kWBlockBytes = kWidth * 128;     // 32 KB per K-block of the weight tile
-constexpr int kSmemA = kNumKBlocks * kABlockBytes;  // 64 KB
 constexpr int kSmemW = kNumKBlocks * kWBlockBytes;  // 128 KB
-constexpr int kSmemBytes = kSmemA + kSmemW + kWidth * 4 + 64;  // + bias + barrier / TMEM slot
 constexpr uint32_t kTmemCols = 256;
+// BM = rows per CTA (UMMA M): the activation tile takes BM * 128 B per K-block
+__host__ __device__ constexpr int smem_a_bytes(int bm) { return kNumKBlocks * bm * 128; }
+__host__ __device__ constexpr int smem_bytes(int bm) { return smem_a_bytes(bm) + kSmemW + kWidth * 4 + 64; }  // + bias + barrier / TMEM slot
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -83,9 +91,116 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
+// physical column of logical column `col` of row `row` in the staged fp32 output tile: a
+// per-row permutation that makes both the epilogue's writes and the row-wise copy-out
+// conflict-free (BM = 128: one row per lane -> XOR with the row; BM = 64: the C-fragment layout
+// has 8 rows x 4 column pairs per instruction -> rotation by 8 (row % 4) + (row / 4) % 2)
+template <int BM>
+__device__ __forceinline__ int out_col(int row, int col) {
+  if (BM == 128) return col ^ (row & 31);
+  return (col + 8 * (row & 3) + ((row >> 2) & 1)) & (kWidth - 1);
+}
+
+__device__ __forceinline__ float bias_act(uint32_t acc, float bias, bool last) {
+  float v = __uint_as_float(acc) + bias;
+  // hidden activations are rounded to bf16 (2^-9) right after: the hardware tanh
+  // approximation (max rel. error 2^-11) is below that resolution
+  if (!last) asm("tanh.approx.f32 %0, %0;" : "+f"(v));
+  return v;
+}
+
+// BM = 128: row = TMEM lane; every warp reads its 32 lanes x 64 columns in two 32-column pieces
+__device__ __forceinline__ void epilogue_m128(uint32_t tmem_base, uint8_t* sA, uint8_t* sW, const float* sBias,
+                                              int q, int cq, int lane, bool last) {
+  constexpr int kABlockBytes = 128 * 128;
+  const int row = q * 32 + lane;
+#pragma unroll 1
+  for (int j = 0; j < 2; ++j) {
+    const int n0 = cq * 64 + j * 32;
+    uint32_t r[32];
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+          "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+          "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = bias_act(r[i], sBias[n0 + i], last);
+    if (!last) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {  // 8 columns = one 16-byte chunk of the next layer's K
+        const int n = n0 + g * 8;
+        uint4 p;
+        p.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+        p.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+        p.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+        p.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+        *reinterpret_cast<uint4*>(sA + swz(kABlockBytes, n >> 6, row, (n & 63) >> 3)) = p;
+      }
+    } else {
+      // last layer: stage the fp32 tile in the (now idle) weight buffer
+      float* sOut = reinterpret_cast<float*>(sW);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sOut[row * kWidth + out_col<128>(row, n0 + i)] = v[i];
+    }
+  }
+}
+
+// BM = 64: rows 16 q .. 16 q + 15 sit in lanes 0..15 of subpartition q; 16x256b.x8 hands thread
+// `lane` the rows lane / 4 (+ 8) and, per repeat j, the column pair 8 j + 2 (lane % 4) + {0, 1}
+// of this warp's 64 columns: 32 elements per thread, all 32 threads busy
+__device__ __forceinline__ void epilogue_m64(uint32_t tmem_base, uint8_t* sA, uint8_t* sW, const float* sBias,
+                                             int q, int cq, int lane, bool last) {
+  constexpr int kABlockBytes = 64 * 128;
+  uint32_t r[32];
+  const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+        "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+  const int row_lo = q * 16 + (lane >> 2), cpair = 2 * (lane & 3);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = cq * 64 + 8 * j + cpair;  // and col + 1
+    const float b0 = sBias[col], b1 = sBias[col + 1];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int row = row_lo + 8 * h;
+      const float v0 = bias_act(r[4 * j + 2 * h], b0, last), v1 = bias_act(r[4 * j + 2 * h + 1], b1, last);
+      if (!last) {
+        // K-block cq, 16-byte chunk j of the next layer's activation row, 4-byte slot lane % 4
+        *reinterpret_cast<uint32_t*>(sA + swz(kABlockBytes, cq, row, j) + 2 * cpair) = pack_bf16(v0, v1);
+      } else {
+        float* sOut = reinterpret_cast<float*>(sW);
+        sOut[row * kWidth + out_col<64>(row, col)] = v0;
+        sOut[row * kWidth + out_col<64>(row, col + 1)] = v1;
+      }
+    }
+  }
+}
+
+template <int kBM>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict__ weights,
                    const float* __restrict__ biases, float* __restrict__ out, long long B, int n_layers) {
+  constexpr int kABlockBytes = kBM * 128;  // per K-block of the activation tile
+  constexpr int kSmemA = smem_a_bytes(kBM);
   // 1024-byte alignment (SWIZZLE_128B atoms) is requested from the compiler / driver; no integer
   // round-up, so that the compiler keeps these pointers in the shared address space (LDS/STS)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -97,6 +212,14 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long m0 = (long long)blockIdx.x * kBM;
+#ifdef TODE_MLP_TIMING
+  long long stamp[16];
+  int n_stamp = 0;
+#define TODE_STAMP() do { if (tid == 0 && n_stamp < 16) stamp[n_stamp++] = clock64(); } while (0)
+#else
+#define TODE_STAMP() do { } while (0)
+#endif
+  TODE_STAMP();
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
@@ -125,8 +248,8 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   load_weights_async(0);
 
   // ---- activation tile: fp32 rows of y -> bf16, swizzled K-major (rows past B are zero) ----
-  constexpr int kAChunks = kBM * (kWidth / 8);  // 4096 chunks of 8 elements, 16 per thread
-  constexpr int kAU = 8;                        // chunks in flight per thread (16 x 16-byte loads)
+  constexpr int kAChunks = kBM * (kWidth / 8);  // chunks of 8 elements
+  constexpr int kAU = kAChunks / kThreads;      // chunks in flight per thread (2 x 16-byte loads each): 8 / 4
 #pragma unroll 1
   for (int base = 0; base < kAChunks; base += kThreads * kAU) {
     float4 v0[kAU], v1[kAU];
@@ -158,6 +281,7 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  TODE_STAMP();  // activation tile loaded
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t idesc = make_idesc(kBM, kWidth);
   const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW), bar = smem_u32(mbar);
@@ -171,6 +295,7 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
     // generic-proxy smem writes (cp.async, st.shared) -> visible to the tensor core (async proxy)
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
+    TODE_STAMP();  // this layer's weights have arrived
 
     if (warp == 0 && lane == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -190,56 +315,17 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
     mbar_wait(bar, parity);
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    TODE_STAMP();  // MMAs done
     // the tensor core is done reading sW: fetch the next layer's weights behind the epilogue
     if (layer + 1 < n_layers) load_weights_async(layer + 1);
 
     // ---- epilogue: TMEM -> registers, + bias, tanh, -> next layer's activation tile / out ----
-    const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter
-    const int row = q * 32 + lane;
     const bool last = layer == n_layers - 1;
-#pragma unroll 1
-    for (int j = 0; j < 2; ++j) {
-      const int n0 = cq * 64 + j * 32;
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)n0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
-            "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
-            "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        v[i] = __uint_as_float(r[i]) + sBias[n0 + i];
-        // hidden activations are rounded to bf16 (2^-9) right after: the hardware tanh
-        // approximation (max rel. error 2^-11) is below that resolution
-        if (!last) asm("tanh.approx.f32 %0, %0;" : "+f"(v[i]));
-      }
-      if (!last) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {  // 8 columns = one 16-byte chunk of the next layer's K
-          const int n = n0 + g * 8;
-          uint4 p;
-          p.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-          p.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-          p.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-          p.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(sA + swz(kABlockBytes, n >> 6, row, (n & 63) >> 3)) = p;
-        }
-      } else {
-        // last layer: stage the fp32 tile in the (now idle) weight buffer, XOR-swizzled by row so
-        // that neither these per-row writes nor the per-column reads below conflict on a bank
-        float* sOut = reinterpret_cast<float*>(sW);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sOut[row * kWidth + ((n0 + i) ^ (row & 31))] = v[i];
-      }
+    const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter
+    if constexpr (kBM == 128) {
+      epilogue_m128(tmem_base, sA, sW, sBias, q, cq, lane, last);
+    } else {
+      epilogue_m64(tmem_base, sA, sW, sBias, q, cq, lane, last);
     }
     if (last) {
       __syncthreads();
@@ -249,14 +335,19 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
         if (m0 + r < B) {
           float* dst = out + (m0 + r) * kWidth;
 #pragma unroll
-          for (int j = 0; j < kWidth / 32; ++j) dst[lane + 32 * j] = sOut[r * kWidth + ((lane + 32 * j) ^ (r & 31))];
+          for (int j = 0; j < kWidth / 32; ++j) dst[lane + 32 * j] = sOut[r * kWidth + out_col<kBM>(r, lane + 32 * j)];
         }
       }
     }
     // TMEM reads and smem writes of this layer are done before the next layer's MMA starts
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
+    TODE_STAMP();  // epilogue done
   }
+#ifdef TODE_MLP_TIMING
+  if (tid == 0 && blockIdx.x == 0)
+    for (int i = 0; i < n_stamp; ++i) reinterpret_cast<long long*>(out)[i] = stamp[i] - stamp[0];
+#endif
 
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -275,15 +366,27 @@ extern "C" int tode_mlp_tanh256_forward(const void* y, const void* weights_bf16,
   if (!al16(y) || !al16(weights_bf16) || !al16(out)) return TODE_EALIGN;
   static bool configured = false;
   if (!configured) {
-    const cudaError_t e = cudaFuncSetAttribute(mlp_tanh256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(mlp_tanh256_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes(128));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mlp_tanh256_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(64));
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const unsigned grid = (unsigned)((B + kBM - 1) / kBM);
-  mlp_tanh256_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float*>(y), static_cast<const __nv_bfloat16*>(weights_bf16),
-      static_cast<const float*>(biases_f32), static_cast<float*>(out), (long long)B, (int)n_layers);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // 128-row tiles unless they would leave SMs idle while 64-row tiles fill more of them
+  if ((B + 127) / 128 >= sms) {
+    mlp_tanh256_kernel<128><<<(unsigned)((B + 127) / 128), kThreads, smem_bytes(128), st>>>(
+        static_cast<const float*>(y), static_cast<const __nv_bfloat16*>(weights_bf16),
+        static_cast<const float*>(biases_f32), static_cast<float*>(out), (long long)B, (int)n_layers);
+  } else {
+    mlp_tanh256_kernel<64><<<(unsigned)((B + 63) / 64), kThreads, smem_bytes(64), st>>>(
+        static_cast<const float*>(y), static_cast<const __nv_bfloat16*>(weights_bf16),
+        static_cast<const float*>(biases_f32), static_cast<float*>(out), (long long)B, (int)n_layers);
+  }
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
