@@ -207,19 +207,15 @@ class C5(Workload):
         return dict(y0=y0, t_start=torch.zeros(batch), t_end=torch.ones(batch), t_eval=None)
 
     def components(self, device=None):
-        kappa = self.KAPPA
+        from torchode_b200.fields import Heat1D
 
-        def field(t, y):
-            out = torch.zeros_like(y)
-            out[:, 1:-1] = kappa * ((y[:, 2:] - 2 * y[:, 1:-1]) + y[:, :-2])
-            return out
-
+        field = Heat1D(self.KAPPA)  # one-pass stencil kernel (bit-identical to the PyTorch expression)
         term = to.ODETerm(field)
         return field, to.Tsit5(term), to.IntegralController(1e-6, 1e-3, term=term)
 
     def describe(self):
-        return ("configs[4]: 1-D heat equation method of lines (PyTorch stencil f), Tsit5+I(1e-6,1e-3), "
-                "batch 64, dim 2^20, fp32, stage-wise route (split-mode finish)")
+        return ("configs[4]: 1-D heat equation method of lines (fields.Heat1D stencil kernel as f), "
+                "Tsit5+I(1e-6,1e-3), batch 64, dim 2^20, fp32, stage-wise route (split-mode finish)")
 
     def algorithmic_bytes(self, batch, T):
         return None

@@ -288,6 +288,13 @@ int tode_interp_eval(const tode_tableau* tab, int32_t data_dtype, int32_t time_d
 int tode_mlp_tanh256_forward(const void* y, const void* weights_bf16, const void* biases_f32,
                              void* out, int64_t B, int32_t n_layers, void* stream);
 
+/* Method-of-lines vector field of the 1-D heat equation with Dirichlet ends (configs[4]), one
+ * HBM pass: out[b,i] = kappa * ((y[b,i+1] - 2 y[b,i]) + y[b,i-1]) for 0 < i < N-1, 0 at the ends;
+ * y, out (B,N) row-major, 16-byte aligned, N divisible by 4 (f32) / 2 (f64).  A user-level f like
+ * the MLP field. */
+int tode_heat1d_forward(const void* y, void* out, int64_t B, int64_t N, double kappa, int32_t dtype,
+                        void* stream);
+
 /* Measurement aid for bench.py (not on the solve path): every thread of a machine-filling
  * grid runs `iters` rounds of 8 independent double-precision FMA chains; writes one double
  * per thread to `sink` (at least tode_bench_fp64_fma_threads() doubles).  Returns the number

@@ -209,9 +209,23 @@ def heat_rhs_torch(kappa):
     return f
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("shape", [(1, 4), (3, 8), (5, 1000), (2, 65536)])
+def test_heat1d_field_kernel_is_bit_identical_to_the_torch_expression(shape, dtype):
+    from torchode_b200.fields import Heat1D
+
+    g = torch.Generator().manual_seed(shape[1])
+    y = torch.randn(*shape, generator=g, dtype=dtype).cuda()
+    field = Heat1D(25.0)
+    got, want = field(None, y), field.forward_reference(None, y)
+    assert bits_equal(got.cpu().numpy(), want.cpu().numpy())
+
+
+@pytest.mark.parametrize("field_kind", ["torch", "kernel"])
 @pytest.mark.parametrize("N", [64, 1024, 4100, 16384])
-def test_staged_opaque_heat_equation_matches_oracle(N):
-    """Config C5 in miniature: method-of-lines heat equation (opaque stencil f), Tsit5 + I."""
+def test_staged_opaque_heat_equation_matches_oracle(N, field_kind):
+    """Config C5 in miniature: method-of-lines heat equation (opaque stencil f -- the PyTorch
+    expression or the one-pass Heat1D kernel), Tsit5 + I."""
     rng = np.random.default_rng(N)
     B = 6
     x = np.linspace(0, 1, N, dtype=np.float32)
@@ -222,7 +236,9 @@ def test_staged_opaque_heat_equation_matches_oracle(N):
     method = to.Tsit5()
     ctrl = to.IntegralController(1e-6, 1e-3)
     want = driver.solve_opaque(heat_rhs_np(kappa), method.to_cabi(), ctrl.to_cabi(5, torch.float32), y0, t0, t1)
-    term = to.ODETerm(heat_rhs_torch(kappa))
+    from torchode_b200.fields import Heat1D
+
+    term = to.ODETerm(heat_rhs_torch(kappa) if field_kind == "torch" else Heat1D(kappa))
     solver = to.AutoDiffAdjoint(to.Tsit5(term), to.IntegralController(1e-6, 1e-3, term=term))
     with torch.no_grad():
         sol = solver.solve(to.InitialValueProblem(cu(y0), cu(t0), cu(t1)))

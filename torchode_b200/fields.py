@@ -132,3 +132,33 @@ class TanhMLP256(nn.Module):
             if layer + 1 < self.n_layers:
                 h = torch.tanh(h).to(torch.bfloat16).to(torch.float32)
         return h
+
+
+class Heat1D(nn.Module):
+    """Method-of-lines field of the 1-D heat equation with Dirichlet ends (BASELINE.json configs[4]):
+    ``out[:, i] = kappa * ((y[:, i+1] - 2 y[:, i]) + y[:, i-1])``, zero at both ends -- one HBM pass in
+    a hand-written kernel (``tode_heat1d_forward``) instead of the five passes of the PyTorch
+    expression.  An ordinary autonomous ``f`` for ``ODETerm`` (stage-wise route);
+    ``forward_reference`` is the same arithmetic, same rounding order, in PyTorch ops."""
+
+    def __init__(self, kappa: float):
+        super().__init__()
+        self.kappa = float(kappa)
+
+    def forward(self, t, y):
+        from . import _launch
+
+        _launch.require_cuda(y)
+        assert y.ndim == 2
+        y = _launch.dense16(y)
+        out = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            _cabi.check(_cabi.lib().tode_heat1d_forward(
+                y.data_ptr(), out.data_ptr(), y.shape[0], y.shape[1], self.kappa, _launch.dtype_id(y.dtype),
+                _launch.stream_ptr(y.device)), "tode_heat1d_forward")
+        return out
+
+    def forward_reference(self, t, y):
+        out = torch.zeros_like(y)
+        out[:, 1:-1] = self.kappa * ((y[:, 2:] - 2 * y[:, 1:-1]) + y[:, :-2])
+        return out
