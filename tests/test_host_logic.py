@@ -237,3 +237,28 @@ def test_term_counts_evaluations_and_passes_args():
     stats = {}
     quiet.init(p, stats)
     assert "n_f_evals" not in stats
+
+
+def test_pow_tables_are_the_generators_output_and_identical_in_both_trees(tmp_path):
+    """csrc/pow_tables.h (kernels) and oracle/pow_tables.h (CPU oracle) must hold the same numbers,
+    and those must be what scripts/gen_pow_tables.py computes (200-bit mpmath, rounded to nearest)."""
+    import importlib.util
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def numbers(path):
+        text = open(path).read()
+        return re.findall(r"0x[0-9a-f]{16}ULL", text)
+
+    a = numbers(os.path.join(root, "torchode_b200", "csrc", "pow_tables.h"))
+    b = numbers(os.path.join(root, "oracle", "pow_tables.h"))
+    assert a == b and len(a) == 1 + 6 + 5 + 4 * 128
+    mpmath = pytest.importorskip("mpmath")  # noqa: F841
+    spec = importlib.util.spec_from_file_location("gen_pow_tables", os.path.join(root, "scripts", "gen_pow_tables.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    out = tmp_path / "pow_tables.h"
+    gen.emit(str(out), "X", *gen.tables())
+    assert numbers(str(out)) == a
