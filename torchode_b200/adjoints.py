@@ -70,6 +70,8 @@ class AutoDiffAdjoint(nn.Module):
         # problem signature, reused by later solves (capture + instantiation cost ~10-50 ms)
         self._plans = {}
         self._rings = {}
+        # solve_from_host: one CUDA stream per chunk and device (host_pipeline.py)
+        self._host_streams = {}
         # handle under which the torch.compile operator finds this solver (compile_ops.py)
         from .compile_ops import solver_handle
 

@@ -57,8 +57,7 @@ def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, devic
     pending: List[Optional[Dict[str, Any]]] = []
     # the chunk streams live with the solver: the caching allocator keeps one pool per stream, fresh
     # streams would mean fresh cudaMallocs on every call
-    cache = solver.__dict__.setdefault("_host_streams", {})
-    streams = cache.setdefault(str(device), [])
+    streams = solver._host_streams.setdefault(str(device), [])
     while len(streams) < chunks:
         streams.append(torch.cuda.Stream(device))
     with torch.no_grad(), torch.cuda.device(device):
