@@ -11,7 +11,8 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_referen
 for w in c1 c3 c4 c5; do
   python bench.py --workload $w --steps 3 --warmup 3 > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
 done
-for w in c2 c1 c3 c4 c5; do
+python bench.py --workload c3 --batch 1048576 --steps 5 --warmup 3 > gpurun_out/bench_c3_2p20.json 2> gpurun_out/bench_c3_2p20.err
+for w in c2 c1 c3 c3_2p20 c4 c5; do
   python -c "
 import json; d=json.load(open('gpurun_out/bench_$w.json')); e=d['e2e']
 print('$w', 'ms/step %.3f' % d['ms_per_step'], 'value %.4g' % d['value'], 'e2e %.4g (%.3f ms)' % (e['value'], e['ms_per_step']), d['route'])"
