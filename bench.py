@@ -618,13 +618,14 @@ def _main(out):
         barrier()
         t_wall = time.perf_counter() - t_wall
         clocks = sampler.stop() if sampler is not None else None
+        timed_route = dict(solver.last_run)  # route / launches of the timed steps
 
         # per-rank accepted steps of ONE step (every step solves the same inputs)
         local = solver.solve(problem)
         acc_local = int(local.stats["n_accepted"].sum())
         attempted_local = int(local.stats["n_steps"].sum())
         iters = (int(local.stats["n_f_evals"][0]) - 2) // 6
-        last_run = dict(solver.last_run)
+        last_run = dict(solver.last_run) if world == 1 else timed_route
         n_status = int((local.status != 0).sum())
         mean_steps = float(local.stats["n_steps"].float().mean())
 
