@@ -551,8 +551,8 @@ def test_solve_from_host_equals_the_device_solve(kind):
     dev_problem = to.InitialValueProblem(host.y0.cuda(), host.t_start.cuda(), host.t_end.cuda(),
                                          None if host.t_eval is None else host.t_eval.cuda())
     want = solver.solve(dev_problem)
-    got = to.solve_from_host(solver, host, "cuda", chunks=3)
-    again = to.solve_from_host(solver, host, "cuda", chunks=7, out=got)  # buffers reused
+    got = to.solve_from_host(solver, host, "cuda", chunks=3, min_chunk=1)
+    again = to.solve_from_host(solver, host, "cuda", chunks=7, min_chunk=1, out=got)  # buffers reused
     assert again.ys.data_ptr() == got.ys.data_ptr()
     for sol in (got, again):
         assert sol.ys.device.type == "cpu" and sol.ys.is_pinned()
@@ -624,7 +624,7 @@ def test_solve_from_host_edge_cases():
     term = to.ODETerm(LotkaVolterra())
     solver = to.AutoDiffAdjoint(to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term))
     host = to.InitialValueProblem(y0.pin_memory(), t_eval=t_eval.pin_memory())
-    got = to.solve_from_host(solver, host, "cuda", chunks=chunks, dt0=dt0)
+    got = to.solve_from_host(solver, host, "cuda", chunks=chunks, min_chunk=1, dt0=dt0)
     n_f = 0
     for c in range(chunks):
         lo, hi = c * 32, (c + 1) * 32

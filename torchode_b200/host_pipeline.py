@@ -26,18 +26,19 @@ def _pinned_like(shape, dtype) -> torch.Tensor:
 
 
 def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, device, *, chunks: int = 8,
-                    dt0: Optional[torch.Tensor] = None, args: Any = None,
+                    min_chunk: int = 4096, dt0: Optional[torch.Tensor] = None, args: Any = None,
                     out: Optional[Solution] = None) -> Solution:
     """``problem``: an InitialValueProblem over CPU tensors (pinned memory makes the copies
     asynchronous).  Returns a Solution over pinned CPU tensors.  ``out``: the Solution of an earlier
     call with the same shapes, whose buffers are reused (allocating pinned memory costs more than a
-    solve)."""
+    solve).  ``min_chunk``: smallest chunk worth a stream of its own (small batches are launch-bound:
+    they run as one chunk)."""
     device = torch.device(device)
     term_ = solver.step_method.term
     assert term_ is not None, "solve_from_host needs the ODE term on the step method"
     B, F, Tn = problem.batch_size, problem.n_features, problem.n_evaluation_points
     D = problem.data_dtype
-    chunks = max(1, min(int(chunks), B)) if B else 1
+    chunks = max(1, min(int(chunks), B // max(1, int(min_chunk)))) if B else 1
     bounds = [shard_bounds(B, i, chunks) for i in range(chunks)]
     reuse = (out is not None and out.ys.shape == (B, max(Tn, 1), F) and out.ys.dtype == D
              and out.ys.is_pinned() and out.status.shape == (B,))

@@ -26,8 +26,7 @@ class InitialValueProblem:
             assert t_eval is not None, "t_end or t_eval is required"
             t_end = t_eval[:, -1]
         self.y0, self.t_start, self.t_end, self.t_eval = y0, t_start, t_end, t_eval
-        # +1 forward in time, -1 backward (t_start == t_end counts as backward, problems.py:42)
-        self.time_direction = torch.where(t_end > t_start, 1, -1)
+        self._time_direction = None
 
         assert y0.ndim == 2, "y0 must be (batch, features)"
         assert t_start.ndim == 1 and t_end.ndim == 1
@@ -39,6 +38,15 @@ class InitialValueProblem:
             assert t_eval.dtype == t_start.dtype
             assert t_eval.shape[0] == t_start.shape[0]
             assert t_eval.device == t_start.device
+
+    @property
+    def time_direction(self) -> torch.Tensor:
+        """+1 forward in time, -1 backward (t_start == t_end counts as backward, problems.py:42).
+        Computed on first use: the kernel routes derive the direction on the device themselves, and
+        three tiny torch launches per problem are a third of a small solve."""
+        if self._time_direction is None:
+            self._time_direction = torch.where(self.t_end > self.t_start, 1, -1)
+        return self._time_direction
 
     data_dtype = property(lambda self: self.y0.dtype)
     time_dtype = property(lambda self: self.t_start.dtype)
