@@ -199,7 +199,11 @@ typedef struct tode_solution {
    * its ys rows as they are produced and its statistics when it finishes -- is ALSO stored at
    * row peer_row0 + b of the gathered buffers of n_peers replicas.  The pointers must be valid
    * on THIS GPU (peer memory mapped over NVLink, e.g. one symmetric-memory allocation per rank;
-   * a replica may be this GPU's own gathered buffer).  peer_global[p] = device int32[4] of
+   * a replica may be this GPU's own gathered buffer).  peer_ys[p] may be NULL: the ys rows are
+   * then not replicated to p by the kernel (dense-output workloads write many small rows; the
+   * caller pushes its finished ys block to the peers in bulk instead).  The four statistics
+   * pointers of a replica may be NULL together (e.g. the caller's own replica when ys / n_steps /
+   * ... above already point into it).  peer_global[p] = device int32[4] of
    * replica p, zeroed before the launch on every rank: after the solve kernel a one-warp
    * epilogue kernel either atomicMax-es this shard's iteration count into [0] of every
    * replica, or -- if this shard needs the failure replay (summary[1] < summary[0]) -- ORs 1

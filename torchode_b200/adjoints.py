@@ -185,11 +185,14 @@ class AutoDiffAdjoint(nn.Module):
         dt0_c = None if dt0 is None else dt0.to(Tt).contiguous()
         prob.dt0 = _launch.ptr(dt0_c)
 
-        ys = torch.empty((B, max(Tn, 1), F), dtype=D, device=dev)
-        n_steps = torch.empty(B, dtype=torch.long, device=dev)
-        n_accepted = torch.empty(B, dtype=torch.long, device=dev)
-        n_init = torch.empty(B, dtype=torch.long, device=dev)
-        status = torch.empty(B, dtype=torch.long, device=dev)
+        if peers is None:
+            ys = torch.empty((B, max(Tn, 1), F), dtype=D, device=dev)
+            n_steps = torch.empty(B, dtype=torch.long, device=dev)
+            n_accepted = torch.empty(B, dtype=torch.long, device=dev)
+            n_init = torch.empty(B, dtype=torch.long, device=dev)
+            status = torch.empty(B, dtype=torch.long, device=dev)
+        else:  # this rank's rows of its own gathered buffers: the kernel writes them exactly once
+            ys, n_steps, n_accepted, n_init, status = peers.own_rows(B, max(Tn, 1), F, D)
         summary = torch.empty(4, dtype=torch.int32, device=dev)
         sol = _cabi.SolutionOut()
         sol.ys, sol.n_steps, sol.n_accepted = ys.data_ptr(), n_steps.data_ptr(), n_accepted.data_ptr()

@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) solve_fused_kernel(const 
     // result row `idx` of this sample: here and into every replica of the gathered buffers
     auto put_row = [&](long long idx, const D* r) {
       store_row<D, F>(ye + idx * F, r);
-      for (int p = 0; p < A.n_peers; ++p) store_row<D, F>(A.p_ys[p] + (A.peer_row0 + b) * row_elems + idx * F, r);
+      for (int p = 0; p < A.n_peers; ++p)
+        if (A.p_ys[p] != nullptr) store_row<D, F>(A.p_ys[p] + (A.peer_row0 + b) * row_elems + idx * F, r);
     };
     T t = ts, dt;
     field(y, k[0]);  // controller.init / ExplicitRungeKutta.init: f0 = f(t_start, y0)
@@ -346,6 +347,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) solve_fused_kernel(const 
     A.n_initialized[b] = Tn > 0 ? cur : 1;
     A.status[b] = status;
     for (int p = 0; p < A.n_peers; ++p) {
+      if (A.p_n_steps[p] == nullptr) continue;
       const long long g = A.peer_row0 + b;
       A.p_n_steps[p][g] = ns;
       A.p_n_accepted[p][g] = nacc;

@@ -79,10 +79,10 @@ int launch_fused(int field, const double* fp, const tode_tableau* tab, const tod
   a.n_peers = sol->n_peers;
   a.peer_row0 = sol->peer_row0;
   for (int p = 0; p < sol->n_peers; ++p) {
-    if (!sol->peer_ys[p] || !sol->peer_n_steps[p] || !sol->peer_n_accepted[p] || !sol->peer_n_initialized[p] ||
-        !sol->peer_status[p] || !sol->peer_global[p])
-      return TODE_EINVAL;
-    if (!aligned_to(sol->peer_ys[p], al)) return TODE_EALIGN;
+    const int n_stats = (sol->peer_n_steps[p] != nullptr) + (sol->peer_n_accepted[p] != nullptr) +
+                        (sol->peer_n_initialized[p] != nullptr) + (sol->peer_status[p] != nullptr);
+    if ((n_stats != 0 && n_stats != 4) || !sol->peer_global[p]) return TODE_EINVAL;
+    if (sol->peer_ys[p] && !aligned_to(sol->peer_ys[p], al)) return TODE_EALIGN;
     a.p_ys[p] = static_cast<D*>(sol->peer_ys[p]);
     a.p_n_steps[p] = reinterpret_cast<long long*>(sol->peer_n_steps[p]);
     a.p_n_accepted[p] = reinterpret_cast<long long*>(sol->peer_n_accepted[p]);
