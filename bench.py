@@ -601,9 +601,12 @@ def _main(out):
         torch.cuda.synchronize()
 
     with torch.no_grad():
-        for _ in range(args.warmup):
-            sol = step()
+        # the clock sampler (an nvidia-smi child polling NVML) starts before the warm-up so that its
+        # start-up does not land in the first timed step; warm-up steps are shaped like timed ones
         sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+        for _ in range(args.warmup):
+            flush_l2(l2buf)
+            sol = step()
         barrier()
         times = []
         t_wall = time.perf_counter()
