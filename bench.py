@@ -254,9 +254,10 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    """nvidia-smi clock / throttle-reason samples during the timed region (the child starts with the
+    warm-up; ``stop(since=...)`` keeps the samples taken after the timed region began)."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -269,7 +270,9 @@ class ClockSampler:
         except OSError:
             pass
 
-    def stop(self):
+    def stop(self, since=None):
+        import datetime
+
         if self.proc is None:
             return None
         self.proc.terminate()
@@ -281,8 +284,16 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         for line in out.strip().splitlines():
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
+            if since is not None:
+                try:
+                    when = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if when < since:
+                        continue
+                except ValueError:
+                    pass
+            parts = parts[1:]
             try:
                 sm.append(float(parts[0]))
                 mx.append(float(parts[1]))
@@ -609,6 +620,7 @@ def _main(out):
             sol = step()
         barrier()
         times = []
+        t_epoch = time.time()
         t_wall = time.perf_counter()
         for _ in range(args.steps):
             flush_l2(l2buf)
@@ -620,7 +632,7 @@ def _main(out):
             times.append(e0.elapsed_time(e1))
         barrier()
         t_wall = time.perf_counter() - t_wall
-        clocks = sampler.stop() if sampler is not None else None
+        clocks = sampler.stop(since=t_epoch - 0.05) if sampler is not None else None
         timed_route = dict(solver.last_run)  # route / launches of the timed steps
 
         # per-rank accepted steps of ONE step (every step solves the same inputs)
