@@ -97,10 +97,11 @@ class SymmetricWorkspace:
     One ``torch.distributed._symmetric_memory`` allocation per rank holds the gathered ``ys``, the
     four gathered int64 statistics and a 4-word global block; every rank maps every other rank's
     allocation over NVLink.  The fused solve kernel of rank r writes the results of its samples
-    into rows ``[r * B_local, (r + 1) * B_local)`` of EVERY rank's buffers while it solves and
-    publishes its iteration count with system-scope atomics: the all-gather that used to follow the
-    solve is gone -- what is left between the ranks is two barriers around the launch (signal
-    pads of the symmetric allocation, stream-ordered, no host sync).
+    into rows ``[r * B_local, (r + 1) * B_local)`` of EVERY rank's buffers while it solves (with
+    ``t_eval`` only the statistics: the dense-output block follows as one bulk copy per peer, see
+    ``bulk_ys``) and publishes its iteration count with system-scope atomics: the all-gather that
+    used to follow the solve is gone -- what is left between the ranks is two barriers around the
+    launch (signal pads of the symmetric allocation, stream-ordered, no host sync).
 
     Equal shard sizes, one node (<= 8 ranks), built-in analytic fields (the fused route) only; the
     returned Solution aliases the workspace -- it is overwritten by the next solve that uses it."""
@@ -140,13 +141,12 @@ class SymmetricWorkspace:
         # pushed to the peers in bulk (one device-to-device copy per peer, each on its own stream).
         self.bulk_ys = self.n_points > 1
         if self.bulk_ys:
-            lo, n = self.rank * local_batch, local_batch * self.n_points * n_features
+            lo = self.rank * local_batch
             self._ys_local = self.ys[lo: lo + local_batch]
             self._ys_peer = [None if p == self.rank else self.hdl.get_buffer(
                 p, (local_batch, self.n_points, n_features), dtype, storage_offset=self._off_ys // esz + lo * self.n_points * n_features)
                 for p in range(self.world)]
             self._push_streams = [torch.cuda.Stream(device) for _ in range(self.world - 1)]
-            del n
         self.barrier()
 
     def matches(self, local_batch, n_points, n_features, dtype) -> bool:
