@@ -757,7 +757,7 @@ def _main(out):
         try:
             peak_fma = measure_fp64_peak(device)  # tera-FMA/s
             # fp64-pipe instructions (DFMA+DMUL+DADD+DSETP) per attempted sample-step of the fused
-            # Tsit5+PID Van der Pol kernel, from the ncu opcode mix (profiles/r01_ncu_fused_c2_v5.txt;
+            # Tsit5+PID Van der Pol kernel, from the ncu opcode mix (profiles/r01_ncu_fused_c2_v6.txt;
             # 328 at the start of round 1, 251 with the branch-free scalar path, 210 with the
             # table-driven pow)
             ops_per_step = 210
@@ -768,8 +768,8 @@ def _main(out):
                 "achieved_tinstr_per_s": achieved, "frac": achieved / peak_fma,
                 "note": "only meaningful for the fp64 workload (c2); counts the lanes that carry a sample "
                         "(a warp runs until its slowest lane is done: 92 % of the lane-steps are useful, "
-                        "the fp64 pipe itself is 68 % busy under ncu; a warp-step costs 2 N_fp64 + N_other = "
-                        "2*210 + 234 issue cycles, the kernel runs at 96 % of that)"}
+                        "the fp64 pipe itself is 71 % busy under ncu; a warp-step costs 2 N_fp64 + N_other = "
+                        "2*210 + 200 issue cycles, the kernel runs at 97 % of that)"}
         except Exception as exc:  # measurement aid only
             line["fp64_issue"] = {"error": str(exc)}
         try:
