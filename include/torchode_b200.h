@@ -299,6 +299,19 @@ int tode_mlp_tanh256_forward(const void* y, const void* weights_bf16, const void
 int tode_heat1d_forward(const void* y, void* out, int64_t B, int64_t N, double kappa, int32_t dtype,
                         void* stream);
 
+/* One whole loop iteration (runge_kutta.py:227-279, step_size_controllers.py:371-429 / 716-774,
+ * adjoints.py:150-201) of a problem whose f is the heat field above, T == 0 (no t_eval): the six stage
+ * combinations, the six stencil evaluations, the error estimate and the per-chunk error norms in ONE
+ * pass over st->y and st->f0 (stage values never leave the SM), then the per-sample controller and the
+ * commit -- three launches, 4 (+4 where accepted) rows of HBM traffic instead of 56.  Replaces
+ * 6 x (tode_erk_stage, tode_heat1d_forward) + tode_erk_finish; same bits.  y1, k_last, y_end: (B,F)
+ * work buffers (16-byte aligned); F divisible by 4 (f32) / 2 (f64); st->scratch as for
+ * tode_erk_finish.  Computes the end-point value only for steps that reach t_end: if any sample ends
+ * with status != SUCCESS, st->y_eval is not meaningful and the caller must re-solve through the
+ * stage-wise entry points. */
+int tode_heat_step(const tode_tableau* tab, const tode_controller* ctrl, const tode_state* st,
+                   double kappa, void* y1, void* k_last, void* y_end, void* stream);
+
 /* Measurement aid for bench.py (not on the solve path): every thread of a machine-filling
  * grid runs `iters` rounds of 8 independent double-precision FMA chains; writes one double
  * per thread to `sink` (at least tode_bench_fp64_fma_threads() doubles).  Returns the number

@@ -249,6 +249,121 @@ def test_staged_opaque_heat_equation_matches_oracle(N, field_kind):
     assert bits_equal(sol.ys.cpu().numpy(), want["ys"])
 
 
+def _heat_problem(B, N, dtype, tdtype, seed, reverse=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.linspace(0, 1, N, dtype=dtype)
+    amp = torch.rand(B, 3, generator=g, dtype=dtype)
+    y0 = sum(amp[:, k - 1:k] * torch.sin(k * torch.pi * x)[None] for k in (1, 2, 3))
+    y0 = y0 + 0.01 * torch.randn(B, N, generator=g, dtype=dtype)  # rough rows: every chunk contributes to the norm
+    t_a = torch.zeros(B, dtype=tdtype)
+    t_b = 0.5 + 0.5 * torch.rand(B, generator=g, dtype=tdtype)  # samples finish at different iterations
+    if reverse:
+        t_a, t_b = t_b, t_a
+    return to.InitialValueProblem(y0.to(DEV), t_a.to(DEV), t_b.to(DEV))
+
+
+def _solve_both_heat_routes(problem, make_solver, dt0=None):
+    out = []
+    for fusion in (True, False):
+        solver = make_solver()
+        solver.use_step_fusion = fusion
+        with torch.no_grad():
+            sol = solver.solve(problem, dt0=dt0)
+        out.append((sol, dict(solver.last_run)))
+    return out
+
+
+def _assert_same_solution(a, b):
+    assert bits_equal(a.ys.cpu().numpy(), b.ys.cpu().numpy())
+    for key in ("n_steps", "n_accepted", "n_initialized", "n_f_evals"):
+        assert a.stats[key].cpu().tolist() == b.stats[key].cpu().tolist(), key
+    assert a.status.cpu().tolist() == b.status.cpu().tolist()
+
+
+HEAT_CASES = [
+    # B, N, data dtype, time dtype, method, controller kind
+    (3, 8, torch.float32, torch.float32, "tsit5", "i"),
+    (5, 1000, torch.float32, torch.float32, "dopri5", "i"),
+    (4, 4100, torch.float32, torch.float32, "tsit5", "pid"),      # 1025 vectors: a one-vector tail chunk
+    (2, 3 * 4096 + 1024 + 4, torch.float32, torch.float32, "tsit5", "i"),  # four chunks, partial last tile
+    (3, 2048 + 6, torch.float64, torch.float64, "tsit5", "i"),    # fp64: 2-element vectors, 2 chunks
+    (3, 5000, torch.float64, torch.float64, "dopri5", "pid"),
+    (2, 4100, torch.float32, torch.float64, "dopri5", "max"),     # mixed dtypes, max norm
+    (2, 2050, torch.float64, torch.float32, "tsit5", "i"),
+    (70, 16384, torch.float32, torch.float32, "tsit5", "i"),      # the split-finish shape of the stage-wise route
+]
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+@pytest.mark.parametrize("B,N,dtype,tdtype,method,kind", HEAT_CASES)
+def test_step_fused_heat_route_is_bit_identical_to_the_stage_wise_route(B, N, dtype, tdtype, method, kind, reverse):
+    """tode_heat_step (whole iteration in one pass, stage values on chip) against 6 x (stage kernel,
+    Heat1D kernel) + finish kernel -- which test_staged_opaque_heat_equation_matches_oracle pins on the
+    oracle: every bit of ys and every counter."""
+    from torchode_b200.fields import Heat1D
+
+    problem = _heat_problem(B, N, dtype, tdtype, seed=N + B, reverse=reverse)
+
+    def make_solver():
+        term = to.ODETerm(Heat1D(20.0))
+        step = (to.Tsit5 if method == "tsit5" else to.Dopri5)(term)
+        if kind == "pid":
+            ctrl = to.PIDController(1e-6, 1e-4, 0.2, 0.5, 0.1, term=term)
+        elif kind == "max":
+            ctrl = to.IntegralController(1e-6, 1e-3, term=term, norm=max_norm)
+        else:
+            ctrl = to.IntegralController(1e-6, 1e-3, term=term)
+        return to.AutoDiffAdjoint(step, ctrl)
+
+    (fused, run_f), (staged, run_s) = _solve_both_heat_routes(problem, make_solver)
+    assert run_f["route"] == "step-fused" and run_s["route"] == "staged"
+    assert run_f["iterations"] == run_s["iterations"] > 3
+    assert (fused.status == 0).all()
+    _assert_same_solution(fused, staged)
+
+
+def test_step_fused_heat_route_with_dt0_and_graph_replay():
+    from torchode_b200.fields import Heat1D
+
+    problem = _heat_problem(4, 8192, torch.float32, torch.float32, seed=5)
+    dt0 = torch.full((4,), 1e-4, device=DEV)
+    term = to.ODETerm(Heat1D(20.0))
+
+    def make_solver():
+        return to.AutoDiffAdjoint(to.Tsit5(term), to.IntegralController(1e-6, 1e-3, term=term))
+
+    (fused, run_f), (staged, _) = _solve_both_heat_routes(problem, make_solver, dt0=dt0)
+    assert run_f["route"] == "step-fused"
+    _assert_same_solution(fused, staged)
+    solver = make_solver()
+    solver.use_cuda_graph = True
+    with torch.no_grad():
+        for _ in range(2):  # second solve replays the cached plan
+            sol = solver.solve(problem, dt0=dt0)
+            assert solver.last_run["route"] == "step-fused+graph"
+            _assert_same_solution(sol, staged)
+
+
+@pytest.mark.parametrize("max_steps,dt_min", [(5, None), (None, 0.05)])
+def test_step_fused_heat_route_hands_failing_problems_to_the_stage_wise_route(max_steps, dt_min):
+    """A step that ends with status != SUCCESS has no end-point value in the step-fused kernels: the
+    solve is redone on the stage-wise kernels, so failures look exactly as they do there."""
+    from torchode_b200.fields import Heat1D
+
+    problem = _heat_problem(3, 4100, torch.float32, torch.float32, seed=9)
+    term = to.ODETerm(Heat1D(20.0))
+
+    def make_solver():
+        kw = {} if dt_min is None else {"dt_min": dt_min}
+        return to.AutoDiffAdjoint(to.Tsit5(term), to.IntegralController(1e-6, 1e-3, term=term, **kw),
+                                  max_steps=max_steps)
+
+    (fused, run_f), (staged, run_s) = _solve_both_heat_routes(problem, make_solver)
+    assert run_f["route"] == "staged" == run_s["route"]
+    assert (staged.status != 0).any()
+    _assert_same_solution(fused, staged)
+
+
 def test_general_mode_for_non_monotone_t_eval():
     rng = np.random.default_rng(3)
     B, F = 33, 2

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi, _launch, status_codes
-from .fields import BuiltinField
+from .fields import BuiltinField, Heat1D
 from .problems import InitialValueProblem
 from .single_step_methods import Dopri5, SingleStepMethod, Tsit5
 from .solution import Solution
@@ -64,6 +64,10 @@ class AutoDiffAdjoint(nn.Module):
         #: capturable (no host sync, no data-dependent Python control flow) and free of host side
         #: effects.  Removes the launch latency that dominates small problems.
         self.use_cuda_graph = False
+        #: stage-wise route with the built-in ``fields.Heat1D`` as f and no ``t_eval``: run a whole loop
+        #: iteration as ONE pass over y (stage values and the stencil's neighbours stay on chip,
+        #: ``tode_heat_step``) instead of 6 x (stage kernel, f) + finish.  Same bits.
+        self.use_step_fusion = True
         #: bookkeeping of the last solve: route taken and number of kernels launched through the C-ABI
         self.last_run = {}
         # staged route with use_cuda_graph: persistent buffers + recorded iteration graph per
@@ -234,18 +238,28 @@ class AutoDiffAdjoint(nn.Module):
     # ------------------------------------------------------------------------------------
     # route 2: stage-wise kernels around an opaque f
     # ------------------------------------------------------------------------------------
-    def _solve_staged(self, problem, term_, dt0, args, general: bool = False, record=None) -> Solution:
+    def _step_fusable(self, problem, term_, args, record) -> bool:
+        """Problems whose loop iteration ``tode_heat_step`` covers: the built-in stencil field as a plain
+        ``f(t, y)``, no dense output, rows of whole 16-byte vectors."""
+        vec = 16 // problem.y0.element_size()
+        return (self.use_step_fusion and record is None and type(term_.f) is Heat1D and not term_.with_args
+                and args is None and problem.t_eval is None and problem.n_features % vec == 0
+                and problem.n_features >= 2 * vec)
+
+    def _solve_staged(self, problem, term_, dt0, args, general: bool = False, record=None,
+                      step_fusion: bool = True) -> Solution:
         lib = _cabi.lib()
         method, ctrl = self.step_method, self.step_size_controller
         dev, D, Tt = problem.device, problem.data_dtype, problem.time_dtype
         B, F, Tn = problem.batch_size, problem.n_features, problem.n_evaluation_points
+        step_fusion = step_fusion and self._step_fusable(problem, term_, args, record)
         cab_t = method.to_cabi()
         cab_c = ctrl.to_cabi(method.convergence_order(), D, self.max_steps)
         S = cab_t.n_stages
         plan = None
         if self.use_cuda_graph and record is None:
             te = problem.t_eval
-            key = (str(dev), B, F, Tn, D, Tt, general, id(term_.f), id(args), dt0 is None,
+            key = (str(dev), B, F, Tn, D, Tt, general, step_fusion, id(term_.f), id(args), dt0 is None,
                    None if te is None else (te.stride(0) == 0), bytes(cab_t), bytes(cab_c))
             plan = self._plans.get(key)
             if plan is None:
@@ -308,6 +322,12 @@ class AutoDiffAdjoint(nn.Module):
         stage, finish = lib.tode_erk_stage, lib.tode_erk_finish
         y_stage, t_nodes = st.y_stage, st.t_nodes
 
+        def launch_fused_iteration(stream):
+            rc = lib.tode_heat_step(tab_p, ctrl_p, st_p, term_.f.kappa, y_stage[0].data_ptr(),
+                                    y_stage[1].data_ptr(), y_stage[2].data_ptr(), stream)
+            if rc:
+                _cabi.check(rc, "tode_heat_step")
+
         def launch_iteration(stream):
             for i in range(1, S):
                 y_i = y_stage[i - 1]
@@ -321,6 +341,8 @@ class AutoDiffAdjoint(nn.Module):
             if rc:
                 _cabi.check(rc, "tode_erk_finish")
 
+        if step_fusion:
+            launch_iteration = launch_fused_iteration
         launched = 0
         ctl_host = None
         graph = plan["graph"] if plan is not None else None
@@ -354,11 +376,17 @@ class AutoDiffAdjoint(nn.Module):
         iters = ctl_host[_cabi.CTL_ITERS]
         if record is not None:
             record.snapshot(st)  # state after the last iteration
-        self.last_run = {"route": "staged+graph" if graph is not None else "staged", "iterations": iters,
+        if step_fusion and bool(st.status.any()):
+            # the step-fused kernels compute what an all-successful solve needs (no end-point value
+            # for a step that fails without reaching t_end): redo on the stage-wise kernels
+            return self._solve_staged(problem, term_, dt0, args, general=general, record=record, step_fusion=False)
+        route = "step-fused" if step_fusion else "staged"
+        self.last_run = {"route": route + "+graph" if graph is not None else route, "iterations": iters,
                          "general": general,
                          "iterations_launched": launched,
-                         # 6 stage kernels + finish (3 launches in split mode) per launched iteration, + init
-                         "kernel_launches_min": launched * S + (2 if dt0 is None else 1)}
+                         # 6 stage kernels + finish (3 launches in split mode) per launched iteration
+                         # (step-fused: 3 launches), + init
+                         "kernel_launches_min": launched * (3 if step_fusion else S) + (2 if dt0 is None else 1)}
         # speculative iterations after the stop flag are no-ops on the device
         if plain_term:
             _uniform_stats(term_, problem, stats, n_init_evals + (S - 1) * iters)

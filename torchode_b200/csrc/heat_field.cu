@@ -8,18 +8,13 @@
 #include <stdint.h>
 
 #include "../../include/torchode_b200.h"
+#include "heat_stencil.cuh"
 
 namespace tode {
 namespace heat {
 
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ float stencil(float l, float c, float r, float kappa) {
-  return __fmul_rn(kappa, __fadd_rn(__fsub_rn(r, __fmul_rn(2.0f, c)), l));
-}
-__device__ __forceinline__ double stencil(double l, double c, double r, double kappa) {
-  return __dmul_rn(kappa, __dadd_rn(__dsub_rn(r, __dmul_rn(2.0, c)), l));
-}
 
 // VEC elements (16 bytes) per thread; N % VEC == 0 so a vector never straddles rows
 template <typename D, int VEC>
