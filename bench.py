@@ -215,7 +215,7 @@ class C5(Workload):
 
     def describe(self):
         return ("configs[4]: 1-D heat equation method of lines (fields.Heat1D stencil kernel as f), "
-                "Tsit5+I(1e-6,1e-3), batch 64, dim 2^20, fp32, stage-wise route (split-mode finish)")
+                "Tsit5+I(1e-6,1e-3), batch 64, dim 2^20, fp32, step-fused route (tode_heat_step: one pass per iteration)")
 
     def algorithmic_bytes(self, batch, T):
         return None
@@ -705,13 +705,20 @@ def _main(out):
     # ---- roofline of the dominant kernel (the fused whole-solve kernel) -----------------------
     kernel_ms = statistics.median(times) if world == 1 else ms_per_step
     alg_bytes = workload.algorithmic_bytes(B, T)
+    step_fused = last_run.get("route", "").startswith("step-fused")
     if alg_bytes is None:
         # stage-wise workloads: solver-owned algorithmic traffic = 44 F e per attempted sample-step
         # (DESIGN.md section 4); the user's f is not part of it
         e = 4 if workload.dtype_name == "f32" else 8
         alg_bytes = 44 * int(problem.n_features) * e * attempted_local
+        if step_fused:
+            # step-fused route (tode_heat_step): y and f0 read, y1 and k6 written per attempted step,
+            # the same four rows moved by the commit of an accepted step; f is inside the kernel
+            alg_bytes = int(problem.n_features) * e * (4 * attempted_local + 4 * acc_local)
     roofline = {
         "kernel": "solve_fused_kernel" if last_run.get("route", "").startswith("fused") else
+                  "heat_step_kernel + finish_split_control_kernel + heat_commit_kernel (whole step incl. f)"
+                  if step_fused else
                   "erk_stage_kernel x6 + erk_finish_kernel (whole staged step incl. the user's f)",
         "bound": "hbm", "achieved": alg_bytes / kernel_ms / 1e6,
         "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / kernel_ms / 1e6 / hbm_peak,
@@ -720,7 +727,10 @@ def _main(out):
         "traffic": NCU_DRAM_BYTES.get((workload.name, B)),
         "traffic_source": NCU_DRAM_SOURCE.get((workload.name, B)),
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-        "note": ("whole solve in registers: HBM is touched only for inputs/outputs; for C2 the kernel is "
+        "note": ("one pass over y per loop iteration: stage values, the stencil's neighbours and the error "
+                 "estimate stay on chip (4 rows of traffic per attempted step + 4 per accepted step instead of 56)"
+                 if step_fused else
+                 "whole solve in registers: HBM is touched only for inputs/outputs; for C2 the kernel is "
                  "fp64-issue-bound, see fp64_issue; the HBM-bound kernels of the stage-wise path are in "
                  "roofline_kernels"),
     }

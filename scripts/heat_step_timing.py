@@ -4,6 +4,7 @@ import sys
 
 import torch
 
+sys.path.insert(0, ".")
 import torchode_b200 as to
 from torchode_b200.fields import Heat1D
 

@@ -193,6 +193,61 @@ def test_finish_kernel_one_iteration(dd, td, F, with_t_eval):
     assert ctl[_cabi.CTL_RUNNING] == 0 and ctl[_cabi.CTL_TICKET] == 0  # scratch words reset
 
 
+@pytest.mark.parametrize("dd,td", [("f32", "f32"), ("f64", "f64"), ("f32", "f64")])
+@pytest.mark.parametrize("F", [2, 12, 256, 1000, 9000, 8193, 16384 + 4])
+@pytest.mark.parametrize("mode", ["hairer", "hairer+t_eval", "dt0"])
+def test_init_kernels(dd, td, F, mode):
+    """tode_init_step_a / _b / tode_init_with_dt0 against the oracle: thread-per-sample, warp-per-sample and
+    -- rows of >= 2048 vectors -- the split variants (one warp per chunk, erk_init_split.cuh)."""
+    rng = np.random.default_rng(F + len(mode))
+    B = 200 if F <= 12 else 23
+    D, T = NP[dd], NP[td]
+    method, ctrl = to.Dopri5(), to.PIDController(1e-5, 1e-4, 0.2, 0.5, 0.05)
+    tab = method.to_cabi()
+    cab = ctrl.to_cabi(5, torch.from_numpy(np.zeros(1, D)).dtype)
+    y0 = rng.normal(size=(B, F)).astype(D)
+    y0[3] *= 1e-7  # d0 < 1e-5 branch
+    f0 = rng.normal(size=(B, F)).astype(D)
+    f0[5] = 0      # d1 < 1e-5 branch
+    t_start = rng.uniform(-1, 1, size=B).astype(T)
+    t_end = (t_start + rng.uniform(0.05, 1.0, size=B) * rng.choice([-1, 1], size=B)).astype(T)
+    t_eval = None
+    if mode == "hairer+t_eval":
+        t_eval = (t_start[:, None] + (t_end - t_start)[:, None] * np.linspace(0, 1, 9)[None]).astype(T)
+        t_eval[::3, 0] += (t_end - t_start)[::3] * T(0.01)  # rows whose first point is not t_start
+        t_eval[7, [2, 5]] = t_eval[7, [5, 2]]                # one non-monotone row
+    st = orc.HostState(y0, t_start, t_end, t_eval, pid=True)
+    st.f0[:] = f0
+    st.y_eval[:] = 0
+    g = _gpu_state_like(st, tab, True, t_eval)
+    lib, stream = _cabi.lib(), _launch.stream_ptr(g.device)
+    if mode == "dt0":
+        dt0 = (rng.uniform(1e-3, 2.0, size=B) * np.sign(t_end - t_start)).astype(T)
+        orc.init_with_dt0(tab, cab, st, dt0)
+        _cabi.check(lib.tode_init_with_dt0(C.byref(tab), C.byref(cab), C.byref(g.c), cu(dt0).data_ptr(), stream), "init")
+    else:
+        y1, t1 = np.zeros((B, F), D), np.zeros(B, T)
+        orc.init_step_a(tab, cab, st, y1, t1)
+        y1g, t1g = torch.zeros((B, F), dtype=g.y.dtype, device=DEV), torch.zeros(B, dtype=g.t.dtype, device=DEV)
+        _cabi.check(lib.tode_init_step_a(C.byref(tab), C.byref(cab), C.byref(g.c), y1g.data_ptr(), t1g.data_ptr(),
+                                         stream), "init a")
+        assert bits_equal(y1g.cpu().numpy(), y1) and bits_equal(t1g.cpu().numpy(), t1)
+        f1 = (f0 + 0.1 * rng.normal(size=(B, F))).astype(D)
+        f1[9] = f0[9]  # max(d1, d2) tiny branch needs d1 tiny as well: sample 5 has f0 = 0
+        f1[5] = 0
+        orc.init_step_b(tab, cab, st, f1)
+        _cabi.check(lib.tode_init_step_b(C.byref(tab), C.byref(cab), C.byref(g.c), cu(f1).data_ptr(), stream), "init b")
+    torch.cuda.synchronize()
+    for name in ("t", "dt", "r1", "r2", "running", "n_steps", "n_accepted", "status", "y_eval"):
+        assert bits_equal(getattr(g, name).cpu().numpy(), getattr(st, name)), name
+    if t_eval is not None:
+        assert g.cursor.cpu().numpy().tolist() == st.cursor.tolist()
+    assert bits_equal(g.t_nodes.cpu().numpy()[1:], st.t_nodes[1:])
+    ctl = g.ctl.cpu().numpy()
+    assert ctl[_cabi.CTL_NONMONO] == st.ctl[_cabi.CTL_NONMONO] == (1 if t_eval is not None else 0)
+    assert ctl[_cabi.CTL_STOP] == 0 and ctl[_cabi.CTL_ITERS] == 0
+
+
 def heat_rhs_np(kappa):
     def f(t, y):
         out = np.zeros_like(y)

@@ -541,7 +541,8 @@ struct InitArgs {
   D* y_eval;
   T* t_nodes;
   int* ctl;
-  D* scratch;      // [0,B): dt0, [B,2B): d1
+  D* scratch;      // [0,B): dt0, [B,2B): d1, then the chunk partials of the split mode
+  long long scratch_elems;
   D* y1_out;       // part a
   T* t1_out;       // part a
   const D* f1;     // part b: f(t1, y1), or NULL when the user supplied dt0
@@ -549,6 +550,50 @@ struct InitArgs {
   double e_init;   // 1 / order, pre-rounded to the data dtype
   D sqrt_f;
 };
+
+// dt0 of part a from the first two norms (:467-471)
+template <typename D, typename T>
+TODE_DEV D init_dt0(D d0, D d1, T ts, T te) {
+  const D dt0 = (d0 < (D)1e-5 || d1 < (D)1e-5) ? (D)1e-6 : fdiv(mul((D)0.01, d0), d1);  // :467-468
+  return min_nan(dt0, (D)fabs_(sub(te, ts)));                                             // :471
+}
+
+// signed first step from the third norm (:481-490)
+template <typename D, typename T>
+TODE_DEV T init_dt_from_norm2(const InitArgs<D, T>& A, D nrm2, D dt0, D d1, T dir) {
+  D d2 = fdiv(nrm2, dt0);
+  // only the Integral copy guards dt0 == 0 (:481 vs :826)
+  if (!A.ctrl.pid && dt0 == (D)0) d2 = (D)__longlong_as_double(0x7ff0000000000000LL);
+  const D m = max_nan_nn(d1, d2);
+  D dt1;
+  if (m <= (D)1e-15) {
+    dt1 = max_nan_nn((D)1e-6, mul(dt0, (D)1e-3));
+  } else {
+    // `0.01 / m` is Tensor.__rtruediv__ = m.reciprocal() * 0.01      (:484-488)
+    dt1 = det_pow_t(mul(fdiv((D)1, m), (D)0.01), A.e_init);
+  }
+  return (T)mul((D)dir, min_nan(mul((D)100, dt0), dt1));  // :490
+}
+
+// per-sample state of a fresh solve (adjoints.py:59-126), written by one thread per sample
+template <typename D, typename T>
+TODE_DEV void init_store_sample(const InitArgs<D, T>& A, long long b, T ts, T dt, int cur) {
+  A.t[b] = ts;
+  A.dt[b] = dt;
+  A.running[b] = 1;
+  A.n_steps[b] = 0;
+  A.n_accepted[b] = 0;
+  A.status[b] = 0;
+  if (A.ctrl.pid) {  // PIDState.default :542
+    A.r1[b] = (D)1;
+    A.r2[b] = (D)1;
+  }
+  if (A.cursor != nullptr) A.cursor[b] = cur;
+  if (A.t_nodes != nullptr) {
+#pragma unroll
+    for (int i = 1; i < kStages; ++i) A.t_nodes[(long long)i * A.B + b] = ffma(A.tab.c[i], dt, ts);
+  }
+}
 
 // part a: d0, d1, dt0, y1 = y0 + dir*dt0*f0, t1 = t0 + dir*dt0   (:459-479)
 template <typename D, typename T, int G, int VEC>
@@ -586,8 +631,7 @@ __global__ void __launch_bounds__(kBlock) init_step_a_kernel(const __grid_consta
       ts = A.t_start[b];
       te = A.t_end[b];
     }
-    D dt0 = (d0 < (D)1e-5 || d1 < (D)1e-5) ? (D)1e-6 : fdiv(mul((D)0.01, d0), d1);  // :467-468
-    dt0 = min_nan(dt0, (D)fabs_(sub(te, ts)));                                       // :471
+    const D dt0 = init_dt0<D, T>(d0, d1, ts, te);
     const T dir = dir_of(ts, te);
     const D sdt = mul((D)dir, dt0);
     for (long long it = 0; it < n_it; ++it) {
@@ -613,7 +657,6 @@ __global__ void __launch_bounds__(kBlock) init_step_a_kernel(const __grid_consta
 // The launcher zeroes the control block before this kernel.
 template <typename D, typename T, int G, int VEC>
 __global__ void __launch_bounds__(kBlock) init_step_b_kernel(const __grid_constant__ InitArgs<D, T> A) {
-  constexpr int S = kStages;
   const int lane = threadIdx.x % G;
   const long long gpb = kBlock / G;
   const long long n = A.F / VEC;
@@ -654,18 +697,7 @@ __global__ void __launch_bounds__(kBlock) init_step_b_kernel(const __grid_consta
         dt0 = A.scratch[b];
         d1 = A.scratch[A.B + b];
       }
-      D d2 = fdiv(nrm2, dt0);
-      // only the Integral copy guards dt0 == 0 (:481 vs :826)
-      if (!c.pid && dt0 == (D)0) d2 = (D)__longlong_as_double(0x7ff0000000000000LL);
-      const D m = max_nan_nn(d1, d2);
-      D dt1;
-      if (m <= (D)1e-15) {
-        dt1 = max_nan_nn((D)1e-6, mul(dt0, (D)1e-3));
-      } else {
-        // `0.01 / m` is Tensor.__rtruediv__ = m.reciprocal() * 0.01      (:484-488)
-        dt1 = det_pow_t(mul(fdiv((D)1, m), (D)0.01), A.e_init);
-      }
-      dt = (T)mul((D)dir, min_nan(mul((D)100, dt0), dt1));  // :490
+      dt = init_dt_from_norm2<D, T>(A, nrm2, dt0, d1, dir);
     } else if (act) {
       dt = A.dt0[b];
     }
@@ -694,23 +726,7 @@ __global__ void __launch_bounds__(kBlock) init_step_b_kernel(const __grid_consta
           VecIO<D, VEC>::st(A.y_eval + row + j * VEC, yv);
         }
       }
-      if (lane == 0) {
-        A.t[b] = ts;
-        A.dt[b] = dt;
-        A.running[b] = 1;
-        A.n_steps[b] = 0;
-        A.n_accepted[b] = 0;
-        A.status[b] = 0;
-        if (c.pid) {  // PIDState.default :542
-          A.r1[b] = (D)1;
-          A.r2[b] = (D)1;
-        }
-        if (A.cursor != nullptr) A.cursor[b] = cur;
-        if (A.t_nodes != nullptr) {
-#pragma unroll
-          for (int i = 1; i < S; ++i) A.t_nodes[(long long)i * A.B + b] = ffma(A.tab.c[i], dt, ts);
-        }
-      }
+      if (lane == 0) init_store_sample<D, T>(A, b, ts, dt, cur);
     }
   }
   if (__any_sync(0xffffffffu, nonmono) && (threadIdx.x & 31) == 0) atomicOr(&A.ctl[TODE_CTL_NONMONO], 1);

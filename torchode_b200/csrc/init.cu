@@ -1,6 +1,7 @@
 // C-ABI: initial step size (Hairer heuristic around the user's second f evaluation) and
 // solver-state initialisation.
 #include "api_common.cuh"
+#include "erk_init_split.cuh"
 #include "erk_kernels.cuh"
 
 namespace tode {
@@ -32,13 +33,34 @@ static int fill_init_args(InitArgs<D, T>& a, const tode_tableau* tab, const tode
   a.t_nodes = static_cast<T*>(st->t_nodes);
   a.ctl = st->ctl;
   a.scratch = static_cast<D*>(st->scratch);
+  a.scratch_elems = st->scratch_elems;
   a.e_init = round_exp<D>(1.0 / (double)tab->order);
   a.sqrt_f = (D)std::sqrt((double)st->F);
   return 0;
 }
 
+// few samples x huge rows: one warp per (sample, chunk), two launches per part (erk_init_split.cuh)
+template <typename D, typename T, int VEC, bool PART_B>
+static int launch_init_split(const InitArgs<D, T>& a, long long cpr, cudaStream_t stream) {
+  const unsigned grid = grid_for(a.B * cpr, kBlock / 32, 8);
+  if (PART_B) {
+    init_split_b_partial_kernel<D, T, VEC><<<grid, kBlock, 0, stream>>>(a);
+    init_split_b_finish_kernel<D, T><<<grid_for(a.B, kBlock, 1), kBlock, 0, stream>>>(a, cpr);
+  } else {
+    init_split_a_partial_kernel<D, T, VEC><<<grid, kBlock, 0, stream>>>(a);
+    init_split_a_finish_kernel<D, T, VEC><<<grid, kBlock, 0, stream>>>(a);
+  }
+  return launch_status();
+}
+
 template <typename D, typename T, int VEC, bool PART_B>
 static int launch_init_vec(const InitArgs<D, T>& a, cudaStream_t stream) {
+  // same condition as the split finish (finish_impl.cuh); needs room for the chunk partials
+  const long long n = a.F / VEC;
+  const long long cpr = (n + kChunkVec - 1) / kChunkVec;
+  if (n >= 2 * kChunkVec && a.B < 16LL * sm_count() && a.scratch != nullptr &&
+      a.scratch_elems >= init_split_scratch_need(a.B, cpr))
+    return launch_init_split<D, T, VEC, PART_B>(a, cpr, stream);
   const bool thread_per_sample = geom_lanes(a.F / VEC) == 1;
   const unsigned grid = grid_for(a.B, thread_per_sample ? kBlock : kBlock / 32, 8);
   if (thread_per_sample) {

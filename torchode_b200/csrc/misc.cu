@@ -17,12 +17,13 @@ extern "C" const char* tode_error_string(int code) {
   return "unknown error";
 }
 
-// scratch (data dtype elements): 2*B for the initial step (dt0, d1); split-mode finish: one
-// partial per (sample, 1024-vector chunk) + a 32-byte step record per sample (sized for the
-// narrowest vector / element width so that it holds for every dtype)
+// scratch (data dtype elements): 2*B for the initial step (dt0, d1) + in split mode two partials
+// per (sample, 1024-vector chunk); split-mode finish: one partial per (sample, chunk) + a 32-byte
+// step record per sample (sized for the narrowest vector / element width so that it holds for
+// every dtype)
 extern "C" int64_t tode_scratch_elems(int64_t B, int64_t F) {
   const int64_t chunks = (F + 1023) / 1024;
-  return 2 * B + B * chunks + 8 * B + 64;
+  return 2 * B + 2 * B * chunks + 8 * B + 64;
 }
 
 // ---- measurement aid: peak double-precision FMA issue rate (bench.py roofline) ------------
