@@ -712,12 +712,12 @@ def _main(out):
         e = 4 if workload.dtype_name == "f32" else 8
         alg_bytes = 44 * int(problem.n_features) * e * attempted_local
         if step_fused:
-            # step-fused route (tode_heat_step): y and f0 read, y1 and k6 written per attempted step,
-            # the same four rows moved by the commit of an accepted step; f is inside the kernel
-            alg_bytes = int(problem.n_features) * e * (4 * attempted_local + 4 * acc_local)
+            # step-fused route (tode_heat_step): y and f0 read, y1 and k6 written per attempted step
+            # (accepting a step flips a buffer selector: no commit copy); f is inside the kernel
+            alg_bytes = int(problem.n_features) * e * 4 * attempted_local
     roofline = {
         "kernel": "solve_fused_kernel" if last_run.get("route", "").startswith("fused") else
-                  "heat_step_kernel + finish_split_control_kernel + heat_commit_kernel (whole step incl. f)"
+                  "heat_step_kernel + finish_split_control_kernel (whole step incl. f)"
                   if step_fused else
                   "erk_stage_kernel x6 + erk_finish_kernel (whole staged step incl. the user's f)",
         "bound": "hbm", "achieved": alg_bytes / kernel_ms / 1e6,
@@ -728,7 +728,7 @@ def _main(out):
         "traffic_source": NCU_DRAM_SOURCE.get((workload.name, B)),
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
         "note": ("one pass over y per loop iteration: stage values, the stencil's neighbours and the error "
-                 "estimate stay on chip (4 rows of traffic per attempted step + 4 per accepted step instead of 56)"
+                 "estimate stay on chip (4 rows of traffic per attempted step instead of 56)"
                  if step_fused else
                  "whole solve in registers: HBM is touched only for inputs/outputs; for C2 the kernel is "
                  "fp64-issue-bound, see fp64_issue; the HBM-bound kernels of the stage-wise path are in "

@@ -302,15 +302,18 @@ int tode_heat1d_forward(const void* y, void* out, int64_t B, int64_t N, double k
 /* One whole loop iteration (runge_kutta.py:227-279, step_size_controllers.py:371-429 / 716-774,
  * adjoints.py:150-201) of a problem whose f is the heat field above, T == 0 (no t_eval): the six stage
  * combinations, the six stencil evaluations, the error estimate and the per-chunk error norms in ONE
- * pass over st->y and st->f0 (stage values never leave the SM), then the per-sample controller and the
- * commit -- three launches, 4 (+4 where accepted) rows of HBM traffic instead of 56.  Replaces
- * 6 x (tode_erk_stage, tode_heat1d_forward) + tode_erk_finish; same bits.  y1, k_last, y_end: (B,F)
- * work buffers (16-byte aligned); F divisible by 4 (f32) / 2 (f64); st->scratch as for
- * tode_erk_finish.  Computes the end-point value only for steps that reach t_end: if any sample ends
- * with status != SUCCESS, st->y_eval is not meaningful and the caller must re-solve through the
- * stage-wise entry points. */
+ * pass over y and the FSAL slot (stage values never leave the SM), then the per-sample controller --
+ * two launches, 4 rows of HBM traffic instead of 56.  Replaces 6 x (tode_erk_stage,
+ * tode_heat1d_forward) + tode_erk_finish; same bits.  The state of sample b lives in (st->y, st->f0)
+ * while sel[b] == 0 and in (y_alt, f_alt) while sel[b] == 1: a step reads one pair, writes y1 and
+ * k[S-1] into the other, and accepting it toggles sel[b] (no commit copy).  sel: (B) bytes, zeroed by
+ * the caller before the first iteration; y_alt, f_alt: (B,F), 16-byte aligned; F divisible by 4 (f32)
+ * / 2 (f64); st->scratch as for tode_erk_finish.  st->y_eval receives the value at t_end of every step
+ * that reaches t_end; a step that ends with status != SUCCESS otherwise has no end-point value: if any
+ * sample fails, st->y_eval is not meaningful and the caller must re-solve through the stage-wise
+ * entry points. */
 int tode_heat_step(const tode_tableau* tab, const tode_controller* ctrl, const tode_state* st,
-                   double kappa, void* y1, void* k_last, void* y_end, void* stream);
+                   double kappa, void* y_alt, void* f_alt, uint8_t* sel, void* stream);
 
 /* Measurement aid for bench.py (not on the solve path): every thread of a machine-filling
  * grid runs `iters` rounds of 8 independent double-precision FMA chains; writes one double

@@ -42,7 +42,7 @@ def main():
             run = solver.last_run
             acc = int(sol.stats["n_accepted"].sum())
             att = int(sol.stats["n_steps"].sum())
-            rows = (4 * att + 4 * acc) if fusion else 56 * att
+            rows = 4 * att if fusion else 56 * att
             print(f"{run['route']:>10}: {ms:8.2f} ms / solve, {run['iterations']} iterations ({ms / run['iterations']:.3f} ms each), "
                   f"accepted {acc}, {acc / ms * 1e3:.3e} acc-steps/s, algorithmic {rows * N * 4 / ms / 1e6:.0f} GB/s")
             sols[fusion] = sol

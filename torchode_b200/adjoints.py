@@ -322,9 +322,20 @@ class AutoDiffAdjoint(nn.Module):
         stage, finish = lib.tode_erk_stage, lib.tode_erk_finish
         y_stage, t_nodes = st.y_stage, st.t_nodes
 
+        if step_fusion:
+            # second (y, f0) buffer pair + per-sample selector: an accepted step flips the selector
+            # instead of copying y <- y1, f0 <- k[S-1]
+            y_alt, f_alt = y_stage[0], y_stage[1]
+            if plan is not None and "sel" in plan:
+                sel = plan["sel"].zero_()
+            else:
+                sel = torch.zeros(B, dtype=torch.uint8, device=dev)
+                if plan is not None:
+                    plan["sel"] = sel
+
         def launch_fused_iteration(stream):
-            rc = lib.tode_heat_step(tab_p, ctrl_p, st_p, term_.f.kappa, y_stage[0].data_ptr(),
-                                    y_stage[1].data_ptr(), y_stage[2].data_ptr(), stream)
+            rc = lib.tode_heat_step(tab_p, ctrl_p, st_p, term_.f.kappa, y_alt.data_ptr(), f_alt.data_ptr(),
+                                    sel.data_ptr(), stream)
             if rc:
                 _cabi.check(rc, "tode_heat_step")
 
@@ -385,8 +396,8 @@ class AutoDiffAdjoint(nn.Module):
                          "general": general,
                          "iterations_launched": launched,
                          # 6 stage kernels + finish (3 launches in split mode) per launched iteration
-                         # (step-fused: 3 launches), + init
-                         "kernel_launches_min": launched * (3 if step_fusion else S) + (2 if dt0 is None else 1)}
+                         # (step-fused: 2 launches), + init
+                         "kernel_launches_min": launched * (2 if step_fusion else S) + (2 if dt0 is None else 1)}
         # speculative iterations after the stop flag are no-ops on the device
         if plain_term:
             _uniform_stats(term_, problem, stats, n_init_evals + (S - 1) * iters)

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(kBlock) finish_split_control_kernel(const __gr
         a.cur_new = cur;
       }
       store_sample_scalars<D, T>(A, b, d, dt, ts, te, ns, cur, my_running, my_failed);
+      if (A.flip != nullptr && d.upd) A.flip[b] ^= 1;  // commit by pointer flip (heat_step.cu)
     }
     aux[b] = a;
   }

@@ -183,6 +183,7 @@ struct FinishArgs {
   D sqrt_f;
   D* scratch;  // split (multi-CTA per sample) mode: chunk partials + per-sample step records
   long long scratch_elems;
+  uint8_t* flip;  // step-fused route (heat_step.cu): per-sample buffer selector, toggled where a step is accepted
 };
 
 // butterfly over the G lanes of a sample group (strides 1, 2, ..., G/2)
