@@ -3,7 +3,7 @@
 // per (sample, chunk), three launches per iteration:
 //
 //   finish_split_partial_kernel  9 rows read once: per-chunk sum of squares / max   -> scratch
-//   finish_split_control_kernel  one thread per sample: chunk partials added in ascending
+//   finish_split_control_kernel  one warp per sample: chunk partials added in ascending
 //                                order, controller, commit decision, all per-sample scalars,
 //                                dense-output bookkeeping, termination flag
 //   finish_split_commit_kernel   per chunk: dense output of the crossed t_eval points (re-read),
@@ -35,6 +35,28 @@ TODE_DEV SplitAux<T>* split_aux(const FinishArgs<D, T>& A, long long chunks_per_
   unsigned long long p = reinterpret_cast<unsigned long long>(A.scratch + A.B * chunks_per_row);
   p = (p + 15ull) & ~15ull;
   return reinterpret_cast<SplitAux<T>*>(p);
+}
+
+// Chunk partials of one sample combined in ascending chunk order (RowNorm::flush / result) by a whole
+// warp: the lanes fetch 32 partials at a time (one coalesced load instead of 32 dependent round trips to
+// L2 by a single thread: 21 us -> 3 us per launch at 256 chunks) and every lane adds them in the canonical
+// order through shuffles.  All lanes return the norm.
+template <typename D>
+TODE_DEV D warp_combine_partials(const D* p, long long cpr, int kind, int lane) {
+  D total = (D)0;
+  bool first = true;
+  for (long long base = 0; base < cpr; base += 32) {
+    const long long i = base + lane;
+    const D v = i < cpr ? p[i] : (D)0;
+    const int cnt = cpr - base < 32 ? (int)(cpr - base) : 32;
+    for (int k = 0; k < cnt; ++k) {
+      const D x = __shfl_sync(0xffffffffu, v, k);
+      if (first) total = x;
+      else total = kind == TODE_NORM_MAX ? max_nan_nn(total, x) : add(total, x);
+      first = false;
+    }
+  }
+  return kind == TODE_NORM_MAX ? total : fsqrt(total);
 }
 
 template <typename D, typename T, int VEC>
@@ -88,59 +110,56 @@ __global__ void __launch_bounds__(kBlock) finish_split_partial_kernel(const __gr
   }
 }
 
+// one WARP per sample: the lanes combine the chunk partials, lane 0 does the per-sample scalar work
 template <typename D, typename T>
 __global__ void __launch_bounds__(kBlock) finish_split_control_kernel(const __grid_constant__ FinishArgs<D, T> A,
                                                                         long long cpr) {
   SplitAux<T>* aux = split_aux(A, cpr);
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * kBlock) >> 5;
   if (A.ctl[TODE_CTL_STOP]) {
     // no-op iteration (launched speculatively after the stop): clear the step records so
     // that the commit kernel of this iteration does nothing
-    for (long long b = (long long)blockIdx.x * kBlock + threadIdx.x; b < A.B; b += (long long)gridDim.x * kBlock)
-      aux[b].flags = 0;
+    for (long long b = warp0; b < A.B; b += n_warps)
+      if (lane == 0) aux[b].flags = 0;
     return;
   }
   const CtrlP<D, T>& c = A.ctrl;
   const D* partials = split_partials(A);
   int my_running = 0, my_failed = 0;
-  for (long long b = (long long)blockIdx.x * kBlock + threadIdx.x; b < A.B; b += (long long)gridDim.x * kBlock) {
+  for (long long b = warp0; b < A.B; b += n_warps) {
     SplitAux<T> a;
     a.flags = 0;
     a.cur_old = a.cur_new = 0;
     a.pad = 0;
     a.t0 = (T)0;
     a.dt = (T)0;
-    if (A.running[b]) {
-      const T t0 = A.t[b], dt = A.dt[b], ts = A.t_start[b], te = A.t_end[b];
-      const int ns = A.n_steps[b] + 1;
-      const D r1 = c.pid ? A.r1[b] : (D)1, r2 = c.pid ? A.r2[b] : (D)1;
-      const D* p = partials + b * cpr;
-      D nrm;
-      if (c.norm == TODE_NORM_MAX) {
-        nrm = p[0];
-        for (long long ch = 1; ch < cpr; ++ch) nrm = max_nan_nn(nrm, p[ch]);
-      } else {
-        D total = p[0];
-        for (long long ch = 1; ch < cpr; ++ch) total = add(total, p[ch]);  // ascending chunk order
-        nrm = fsqrt(total);
+    if (A.running[b]) {  // warp-uniform
+      const D nrm = warp_combine_partials<D>(partials + b * cpr, cpr, c.norm, lane);
+      if (lane == 0) {
+        const T t0 = A.t[b], dt = A.dt[b], ts = A.t_start[b], te = A.t_end[b];
+        const int ns = A.n_steps[b] + 1;
+        const D r1 = c.pid ? A.r1[b] : (D)1, r2 = c.pid ? A.r2[b] : (D)1;
+        const Decision<D, T> d = decide_step<D, T>(c, nrm, t0, dt, ts, te, r1, r2, ns, true);
+        int cur = 0;
+        a.flags = 1 | (d.upd ? 2 : 0);
+        a.t0 = t0;
+        a.dt = dt;
+        if (A.Tn == 0) {
+          if (!d.running_new || d.status != TODE_SUCCESS) a.flags |= 4;
+        } else {
+          const T* tev = A.t_eval + b * A.te_stride;
+          cur = A.cursor[b];
+          a.cur_old = cur;
+          while (cur < A.Tn && ffma(d.dir, d.t_new, mul(-d.dir, tev[cur])) >= (T)0) ++cur;  // :216-223
+          a.cur_new = cur;
+        }
+        store_sample_scalars<D, T>(A, b, d, dt, ts, te, ns, cur, my_running, my_failed);
+        if (A.flip != nullptr && d.upd) A.flip[b] ^= 1;  // commit by pointer flip (heat_step.cu)
       }
-      const Decision<D, T> d = decide_step<D, T>(c, nrm, t0, dt, ts, te, r1, r2, ns, true);
-      int cur = 0;
-      a.flags = 1 | (d.upd ? 2 : 0);
-      a.t0 = t0;
-      a.dt = dt;
-      if (A.Tn == 0) {
-        if (!d.running_new || d.status != TODE_SUCCESS) a.flags |= 4;
-      } else {
-        const T* tev = A.t_eval + b * A.te_stride;
-        cur = A.cursor[b];
-        a.cur_old = cur;
-        while (cur < A.Tn && ffma(d.dir, d.t_new, mul(-d.dir, tev[cur])) >= (T)0) ++cur;  // :216-223
-        a.cur_new = cur;
-      }
-      store_sample_scalars<D, T>(A, b, d, dt, ts, te, ns, cur, my_running, my_failed);
-      if (A.flip != nullptr && d.upd) A.flip[b] ^= 1;  // commit by pointer flip (heat_step.cu)
     }
-    aux[b] = a;
+    if (lane == 0) aux[b] = a;
   }
   publish_termination(A.ctl, my_running, my_failed);
 }

@@ -25,7 +25,7 @@ static int launch_finish_split(const FinishArgs<D, T>& a, cudaStream_t stream) {
   if (a.scratch == nullptr || a.scratch_elems < need) return TODE_EINVAL;
   const unsigned grid = grid_for(a.B * cpr, kBlock / 32, 8);
   finish_split_partial_kernel<D, T, VEC><<<grid, kBlock, 0, stream>>>(a);
-  finish_split_control_kernel<D, T><<<grid_for(a.B, kBlock, 1), kBlock, 0, stream>>>(a, cpr);
+  finish_split_control_kernel<D, T><<<grid_for(a.B, kBlock / 32, 1), kBlock, 0, stream>>>(a, cpr);
   finish_split_commit_kernel<D, T, VEC><<<grid, kBlock, 0, stream>>>(a);
   return launch_status();
 }
