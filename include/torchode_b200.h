@@ -292,6 +292,15 @@ int tode_interp_eval(const tode_tableau* tab, int32_t data_dtype, int32_t time_d
 int tode_mlp_tanh256_forward(const void* y, const void* weights_bf16, const void* biases_f32,
                              void* out, int64_t B, int32_t n_layers, void* stream);
 
+/* Stage-fused evaluation: out = MLP(y_i) with y_i = st->y + st->dt * sum_{j<stage} a[stage][j] k[j]
+ * (runge_kutta.py:259-263) formed while the kernel loads its activation tile -- one launch instead of
+ * tode_erk_stage + tode_mlp_tanh256_forward, same bits (y_i is never written unless y_out != NULL:
+ * pass the last stage's y_out, which tode_erk_finish needs as y1).  st->F == 256, data dtype f32;
+ * k[j], y_out, out 16-byte aligned; a no-op once st->ctl (if non-NULL) carries the stop flag. */
+int tode_mlp_tanh256_stage_forward(const tode_tableau* tab, int stage, const tode_state* st,
+                                   const void* const* k, void* y_out, const void* weights_bf16,
+                                   const void* biases_f32, void* out, int32_t n_layers, void* stream);
+
 /* Method-of-lines vector field of the 1-D heat equation with Dirichlet ends (configs[4]), one
  * HBM pass: out[b,i] = kappa * ((y[b,i+1] - 2 y[b,i]) + y[b,i-1]) for 0 < i < N-1, 0 at the ends;
  * y, out (B,N) row-major, 16-byte aligned, N divisible by 4 (f32) / 2 (f64).  A user-level f like

@@ -71,3 +71,71 @@ def test_solve_around_the_mlp_field_matches_the_oracle_loop():
     assert int(sol.stats["n_f_evals"][0]) == want["n_f_evals"]
     assert bits_equal(sol.ys.cpu().numpy(), want["ys"])
     assert (sol.status == 0).all() and int(sol.stats["n_steps"].max()) >= 5
+
+
+@pytest.mark.parametrize("B", [37, 8192, 19000])  # 64-row and 128-row tiles
+@pytest.mark.parametrize("tdtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("method", [to.Dopri5, to.Tsit5])
+def test_stage_fused_evaluation_equals_stage_kernel_then_field(B, tdtype, method):
+    """tode_mlp_tanh256_stage_forward (stage combination formed inside the kernel's operand load) against
+    tode_erk_stage followed by tode_mlp_tanh256_forward: every bit of f's output and of the stored y_i."""
+    import ctypes as C
+
+    from torchode_b200 import _cabi, _launch
+
+    field = make_field(3)
+    tab = method().to_cabi()
+    g = torch.Generator().manual_seed(B)
+    y = torch.randn(B, 256, generator=g).to(DEV)
+    ks = [torch.randn(B, 256, generator=g).to(DEV) for _ in range(6)]
+    dt = (0.01 + 0.1 * torch.rand(B, generator=g, dtype=tdtype)).to(DEV)
+    st = _launch._minimal_state(y, dt)
+    lib, stream = _cabi.lib(), _launch.stream_ptr(y.device)
+    for stage in range(1, 7):
+        y_i = _launch.erk_stage(tab, stage, y, dt, ks[:stage])
+        want = field(None, y_i)
+        for store in (False, True):
+            y_out = torch.full_like(y, float("nan"))
+            got = torch.empty_like(y)
+            _cabi.check(lib.tode_mlp_tanh256_stage_forward(
+                C.byref(tab), stage, C.byref(st), _launch.kptrs(ks[:stage]), y_out.data_ptr() if store else None,
+                field.weights.data_ptr(), field.biases.data_ptr(), got.data_ptr(), field.n_layers, stream), "stage mlp")
+            torch.cuda.synchronize()
+            assert bits_equal(got.cpu().numpy(), want.cpu().numpy()), (stage, store)
+            if store:
+                assert bits_equal(y_out.cpu().numpy(), y_i.cpu().numpy()), stage
+    # a set stop flag turns the launch into a no-op
+    ctl = torch.zeros(_cabi.CTL_WORDS, dtype=torch.int32, device=DEV)
+    ctl[_cabi.CTL_STOP] = 1
+    st.ctl = ctl.data_ptr()
+    got = torch.full_like(y, 7.0)
+    _cabi.check(lib.tode_mlp_tanh256_stage_forward(
+        C.byref(tab), 3, C.byref(st), _launch.kptrs(ks[:3]), None, field.weights.data_ptr(),
+        field.biases.data_ptr(), got.data_ptr(), field.n_layers, stream), "stage mlp")
+    torch.cuda.synchronize()
+    assert (got == 7.0).all()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_stage_fused_route_is_bit_identical_to_the_stage_wise_route(graph):
+    field = make_field(3)
+    B = 700
+    g = torch.Generator().manual_seed(11)
+    problem = to.InitialValueProblem(torch.randn(B, 256, generator=g).to(DEV), torch.zeros(B, device=DEV),
+                                     (0.5 + torch.rand(B, generator=g)).to(DEV))
+    term = to.ODETerm(field)
+    sols = {}
+    for fusion in (True, False):
+        solver = to.AutoDiffAdjoint(to.Dopri5(term), to.IntegralController(1e-6, 1e-3, term=term))
+        solver.use_step_fusion = fusion
+        solver.use_cuda_graph = graph
+        with torch.no_grad():
+            for _ in range(2 if graph else 1):  # second solve replays the cached plan
+                sols[fusion] = solver.solve(problem)
+        want_route = ("stage-fused" if fusion else "staged") + ("+graph" if graph else "")
+        assert solver.last_run["route"] == want_route
+    a, b = sols[True], sols[False]
+    assert bits_equal(a.ys.cpu().numpy(), b.ys.cpu().numpy())
+    for key in ("n_steps", "n_accepted", "n_f_evals"):
+        assert a.stats[key].cpu().tolist() == b.stats[key].cpu().tolist()
+    assert (a.status == 0).all() and int(a.stats["n_steps"].max()) >= 5

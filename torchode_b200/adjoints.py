@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi, _launch, status_codes
-from .fields import BuiltinField, Heat1D
+from .fields import BuiltinField, Heat1D, TanhMLP256
 from .problems import InitialValueProblem
 from .single_step_methods import Dopri5, SingleStepMethod, Tsit5
 from .solution import Solution
@@ -48,6 +48,11 @@ def _uniform_stats(term_, problem, stats: Dict[str, Any], n_f_evals: int):
         stats["n_f_evals"].fill_(n_f_evals)
 
 
+def plain_mlp_term(term_) -> bool:
+    """A plain ODETerm around f(t, y): nothing but the evaluation count depends on the calls of f."""
+    return type(term_) is ODETerm and not term_.with_args
+
+
 class AutoDiffAdjoint(nn.Module):
     def __init__(self, step_method: SingleStepMethod, step_size_controller: StepSizeController, *,
                  max_steps: Optional[int] = None, backprop_through_step_size_control: bool = True):
@@ -66,7 +71,9 @@ class AutoDiffAdjoint(nn.Module):
         self.use_cuda_graph = False
         #: stage-wise route with the built-in ``fields.Heat1D`` as f and no ``t_eval``: run a whole loop
         #: iteration as ONE pass over y (stage values and the stencil's neighbours stay on chip,
-        #: ``tode_heat_step``) instead of 6 x (stage kernel, f) + finish.  Same bits.
+        #: ``tode_heat_step``) instead of 6 x (stage kernel, f) + finish.  With ``fields.TanhMLP256`` as
+        #: f: every stage combination is formed inside the MLP kernel's operand load
+        #: (``tode_mlp_tanh256_stage_forward``) instead of a stage kernel of its own.  Same bits.
         self.use_step_fusion = True
         #: bookkeeping of the last solve: route taken and number of kernels launched through the C-ABI
         self.last_run = {}
@@ -253,13 +260,16 @@ class AutoDiffAdjoint(nn.Module):
         dev, D, Tt = problem.device, problem.data_dtype, problem.time_dtype
         B, F, Tn = problem.batch_size, problem.n_features, problem.n_evaluation_points
         step_fusion = step_fusion and self._step_fusable(problem, term_, args, record)
+        stage_fusion = (self.use_step_fusion and record is None and type(term_.f) is TanhMLP256 and plain_mlp_term(term_)
+                        and args is None and D == torch.float32 and F == TanhMLP256.WIDTH
+                        and term_.f.weights.device == dev)
         cab_t = method.to_cabi()
         cab_c = ctrl.to_cabi(method.convergence_order(), D, self.max_steps)
         S = cab_t.n_stages
         plan = None
         if self.use_cuda_graph and record is None:
             te = problem.t_eval
-            key = (str(dev), B, F, Tn, D, Tt, general, step_fusion, id(term_.f), id(args), dt0 is None,
+            key = (str(dev), B, F, Tn, D, Tt, general, step_fusion, stage_fusion, id(term_.f), id(args), dt0 is None,
                    None if te is None else (te.stride(0) == 0), bytes(cab_t), bytes(cab_c))
             plan = self._plans.get(key)
             if plan is None:
@@ -339,6 +349,24 @@ class AutoDiffAdjoint(nn.Module):
             if rc:
                 _cabi.check(rc, "tode_heat_step")
 
+        def launch_mlp_iteration(stream):
+            # fields.TanhMLP256: the stage combination is formed while the tcgen05 kernel loads its
+            # activation tile (tode_mlp_tanh256_stage_forward) -- no stage kernel, y_i is only stored
+            # for the last stage (the finish kernel's y1)
+            mlp = term_.f
+            for i in range(1, S):
+                k_i = torch.empty_like(st.y)
+                y_out = y_stage[S - 2].data_ptr() if i == S - 1 else None
+                rc = lib.tode_mlp_tanh256_stage_forward(tab_p, i, st_p, kp, y_out, mlp.weights.data_ptr(),
+                                                        mlp.biases.data_ptr(), k_i.data_ptr(), mlp.n_layers, stream)
+                if rc:
+                    _cabi.check(rc, "tode_mlp_tanh256_stage_forward")
+                ks[i] = k_i  # keep alive until the finish kernel has consumed it
+                kp[i] = k_i.data_ptr()
+            rc = finish(tab_p, ctrl_p, st_p, kp, y_stage[S - 2].data_ptr(), stream)
+            if rc:
+                _cabi.check(rc, "tode_erk_finish")
+
         def launch_iteration(stream):
             for i in range(1, S):
                 y_i = y_stage[i - 1]
@@ -354,6 +382,8 @@ class AutoDiffAdjoint(nn.Module):
 
         if step_fusion:
             launch_iteration = launch_fused_iteration
+        elif stage_fusion:
+            launch_iteration = launch_mlp_iteration
         launched = 0
         ctl_host = None
         graph = plan["graph"] if plan is not None else None
@@ -391,7 +421,7 @@ class AutoDiffAdjoint(nn.Module):
             # the step-fused kernels compute what an all-successful solve needs (no end-point value
             # for a step that fails without reaching t_end): redo on the stage-wise kernels
             return self._solve_staged(problem, term_, dt0, args, general=general, record=record, step_fusion=False)
-        route = "step-fused" if step_fusion else "staged"
+        route = "step-fused" if step_fusion else ("stage-fused" if stage_fusion else "staged")
         self.last_run = {"route": route + "+graph" if graph is not None else route, "iterations": iters,
                          "general": general,
                          "iterations_launched": launched,

@@ -195,10 +195,29 @@ __device__ __forceinline__ void epilogue_m64(uint32_t tmem_base, uint8_t* sA, ui
   }
 }
 
+// Stage-fused evaluation (tode_mlp_tanh256_stage_forward): the rows handed to the MLP are not read
+// from memory but formed while the activation tile is loaded,
+//   y_i = y + dt * sum_{j < nk} a[j] * k[j]        (runge_kutta.py:259-263)
+// with the arithmetic of erk_stage_kernel (product, FMA chain in ascending j, one FMA with dt), so
+// that the launch replaces tode_erk_stage + tode_mlp_tanh256_forward bit for bit.  nk == 0: plain
+// evaluation of y.
+constexpr int kMaxStageK = 6;
+struct StageIn {
+  const float* k[kMaxStageK];
+  float a[kMaxStageK];
+  const void* dt;     // (B) per-sample step, float or double
+  float* y_out;       // (B,256) or NULL: where y_i is also stored (the last stage's y_i is the step's y1)
+  const int* ctl;     // control block or NULL: the launch is a no-op once the stop flag is set
+  int nk;
+  int dt_is_f64;
+};
+
 template <int kBM>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict__ weights,
-                   const float* __restrict__ biases, float* __restrict__ out, long long B, int n_layers) {
+                   const float* __restrict__ biases, float* __restrict__ out, long long B, int n_layers,
+                   const __grid_constant__ StageIn sp) {
+  if (sp.ctl != nullptr && sp.ctl[TODE_CTL_STOP]) return;  // speculative iteration after the stop
   constexpr int kABlockBytes = kBM * 128;  // per K-block of the activation tile
   constexpr int kSmemA = smem_a_bytes(kBM);
   // 1024-byte alignment (SWIZZLE_128B atoms) is requested from the compiler / driver; no integer
@@ -250,6 +269,60 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   // ---- activation tile: fp32 rows of y -> bf16, swizzled K-major (rows past B are zero) ----
   constexpr int kAChunks = kBM * (kWidth / 8);  // chunks of 8 elements
   constexpr int kAU = kAChunks / kThreads;      // chunks in flight per thread (2 x 16-byte loads each): 8 / 4
+  if (sp.nk > 0) {
+    // one 8-element chunk per thread and round; every operand row's two 16-byte loads are issued
+    // before the first use (up to 14 loads in flight per thread)
+#pragma unroll 1
+    for (int base = 0; base < kAChunks; base += kThreads) {
+      const int idx = base + tid;
+      const int row = idx / (kWidth / 8), chunk = idx % (kWidth / 8);
+      float r[8];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) r[x] = 0.f;
+      if (m0 + row < B) {
+        const size_t off = (size_t)(m0 + row) * kWidth + chunk * 8;
+        float4 yv[2], kv[kMaxStageK][2];
+        yv[0] = *reinterpret_cast<const float4*>(y + off);
+        yv[1] = *reinterpret_cast<const float4*>(y + off + 4);
+#pragma unroll
+        for (int j = 0; j < kMaxStageK; ++j) {
+          if (j < sp.nk) {
+            kv[j][0] = *reinterpret_cast<const float4*>(sp.k[j] + off);
+            kv[j][1] = *reinterpret_cast<const float4*>(sp.k[j] + off + 4);
+          }
+        }
+        const float dtr = sp.dt_is_f64 ? (float)static_cast<const double*>(sp.dt)[m0 + row]
+                                       : static_cast<const float*>(sp.dt)[m0 + row];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float yy[4] = {yv[h].x, yv[h].y, yv[h].z, yv[h].w};
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < kMaxStageK; ++j) {
+              if (j < sp.nk) {
+                const float4 kk = kv[j][h];
+                const float kx = x == 0 ? kk.x : (x == 1 ? kk.y : (x == 2 ? kk.z : kk.w));
+                acc = j == 0 ? __fmul_rn(sp.a[0], kx) : __fmaf_rn(sp.a[j], kx, acc);
+              }
+            }
+            r[h * 4 + x] = __fmaf_rn(dtr, acc, yy[x]);
+          }
+        }
+        if (sp.y_out != nullptr) {
+          *reinterpret_cast<float4*>(sp.y_out + off) = make_float4(r[0], r[1], r[2], r[3]);
+          *reinterpret_cast<float4*>(sp.y_out + off + 4) = make_float4(r[4], r[5], r[6], r[7]);
+        }
+      }
+      uint4 p;
+      p.x = pack_bf16(r[0], r[1]);
+      p.y = pack_bf16(r[2], r[3]);
+      p.z = pack_bf16(r[4], r[5]);
+      p.w = pack_bf16(r[6], r[7]);
+      *reinterpret_cast<uint4*>(sA + swz(kABlockBytes, chunk >> 3, row, chunk & 7)) = p;
+    }
+  } else {
 #pragma unroll 1
   for (int base = 0; base < kAChunks; base += kThreads * kAU) {
     float4 v0[kAU], v1[kAU];
@@ -276,6 +349,7 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
       p.w = pack_bf16(v1[u].z, v1[u].w);
       *reinterpret_cast<uint4*>(sA + swz(kABlockBytes, chunk >> 3, row, chunk & 7)) = p;
     }
+  }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -357,9 +431,11 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
 }  // namespace mlp
 }  // namespace tode
 
-extern "C" int tode_mlp_tanh256_forward(const void* y, const void* weights_bf16, const void* biases_f32,
-                                        void* out, int64_t B, int32_t n_layers, void* stream) {
-  using namespace tode::mlp;
+namespace tode {
+namespace mlp {
+
+static int launch_mlp(const float* y, const void* weights_bf16, const void* biases_f32, void* out, int64_t B,
+                      int32_t n_layers, const StageIn& sp, void* stream) {
   if (!y || !weights_bf16 || !biases_f32 || !out || n_layers < 1 || n_layers > 8) return TODE_EINVAL;
   if (B == 0) return 0;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -380,13 +456,46 @@ extern "C" int tode_mlp_tanh256_forward(const void* y, const void* weights_bf16,
   // 128-row tiles unless they would leave SMs idle while 64-row tiles fill more of them
   if ((B + 127) / 128 >= sms) {
     mlp_tanh256_kernel<128><<<(unsigned)((B + 127) / 128), kThreads, smem_bytes(128), st>>>(
-        static_cast<const float*>(y), static_cast<const __nv_bfloat16*>(weights_bf16),
-        static_cast<const float*>(biases_f32), static_cast<float*>(out), (long long)B, (int)n_layers);
+        y, static_cast<const __nv_bfloat16*>(weights_bf16), static_cast<const float*>(biases_f32),
+        static_cast<float*>(out), (long long)B, (int)n_layers, sp);
   } else {
     mlp_tanh256_kernel<64><<<(unsigned)((B + 63) / 64), kThreads, smem_bytes(64), st>>>(
-        static_cast<const float*>(y), static_cast<const __nv_bfloat16*>(weights_bf16),
-        static_cast<const float*>(biases_f32), static_cast<float*>(out), (long long)B, (int)n_layers);
+        y, static_cast<const __nv_bfloat16*>(weights_bf16), static_cast<const float*>(biases_f32),
+        static_cast<float*>(out), (long long)B, (int)n_layers, sp);
   }
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace mlp
+}  // namespace tode
+
+extern "C" int tode_mlp_tanh256_forward(const void* y, const void* weights_bf16, const void* biases_f32,
+                                        void* out, int64_t B, int32_t n_layers, void* stream) {
+  tode::mlp::StageIn sp{};
+  return tode::mlp::launch_mlp(static_cast<const float*>(y), weights_bf16, biases_f32, out, B, n_layers, sp, stream);
+}
+
+extern "C" int tode_mlp_tanh256_stage_forward(const tode_tableau* tab, int stage, const tode_state* st,
+                                              const void* const* k, void* y_out, const void* weights_bf16,
+                                              const void* biases_f32, void* out, int32_t n_layers, void* stream) {
+  using namespace tode::mlp;
+  if (!tab || !st || !k || !st->y || !st->dt) return TODE_EINVAL;
+  if (stage < 1 || stage >= tab->n_stages || stage > kMaxStageK) return TODE_EINVAL;
+  if (st->F != kWidth || st->data_dtype != TODE_F32) return TODE_ENOSUP;
+  if (st->time_dtype != TODE_F32 && st->time_dtype != TODE_F64) return TODE_EINVAL;
+  StageIn sp{};
+  for (int j = 0; j < stage; ++j) {
+    if (!k[j]) return TODE_EINVAL;
+    if (reinterpret_cast<uintptr_t>(k[j]) & 15) return TODE_EALIGN;
+    sp.k[j] = static_cast<const float*>(k[j]);
+    sp.a[j] = (float)tab->a[stage][j];  // ButcherTableau.to(data dtype), as tode_erk_stage
+  }
+  if (y_out && (reinterpret_cast<uintptr_t>(y_out) & 15)) return TODE_EALIGN;
+  sp.dt = st->dt;
+  sp.y_out = static_cast<float*>(y_out);
+  sp.ctl = st->ctl;
+  sp.nk = stage;
+  sp.dt_is_f64 = st->time_dtype == TODE_F64;
+  return launch_mlp(static_cast<const float*>(st->y), weights_bf16, biases_f32, out, st->B, n_layers, sp, stream);
 }
