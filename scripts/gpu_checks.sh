@@ -22,3 +22,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:solve_fused -s 1 -c 1 -o gpurun_out/prof_fused_c2 -f \
   python scripts/profile_kernels.py c2 > gpurun_out/ncu_fused.log 2>&1
 tail -1 gpurun_out/ncu_fused.log
+# configs[4]: launch list of one step-fused solve and a full capture of heat_step_kernel
+ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/launches_c5.csv \
+  python scripts/profile_kernels.py c5 > gpurun_out/ncu_c5_list.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:heat_step -s 10 -c 1 -o gpurun_out/prof_heat_step -f \
+  python scripts/profile_kernels.py c5 > gpurun_out/ncu_heat_step.log 2>&1
+tail -1 gpurun_out/ncu_heat_step.log
