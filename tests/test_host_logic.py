@@ -262,3 +262,48 @@ def test_pow_tables_are_the_generators_output_and_identical_in_both_trees(tmp_pa
     out = tmp_path / "pow_tables.h"
     gen.emit(str(out), "X", *gen.tables())
     assert numbers(str(out)) == a
+
+
+def test_route_predicates_of_the_fused_step_and_stage_routes():
+    """Which problems the step-fused (fields.Heat1D) route takes -- host logic only, no kernel runs."""
+    from torchode_b200.adjoints import plain_mlp_term
+    from torchode_b200.fields import Heat1D
+
+    term = to.ODETerm(Heat1D(25.0))
+    solver = to.AutoDiffAdjoint(to.Tsit5(term), to.IntegralController(1e-6, 1e-3, term=term))
+    y0 = torch.zeros(3, 4096)
+    t0, t1 = torch.zeros(3), torch.ones(3)
+    plain = to.InitialValueProblem(y0, t0, t1)
+    assert solver._step_fusable(plain, term, None, None)
+    assert not solver._step_fusable(plain, term, ("args",), None)                 # f(t, y, args)
+    assert not solver._step_fusable(plain, term, None, object())                  # recorded (autograd) solve
+    with_t_eval = to.InitialValueProblem(y0, t0, t1, torch.linspace(0, 1, 5).expand(3, -1))
+    assert not solver._step_fusable(with_t_eval, term, None, None)                # dense output: stage-wise kernels
+    ragged = to.InitialValueProblem(torch.zeros(3, 4098 + 1), t0, t1)
+    assert not solver._step_fusable(ragged, term, None, None)                     # rows of whole 16-byte vectors only
+    tiny = to.InitialValueProblem(torch.zeros(3, 4), t0, t1)
+    assert not solver._step_fusable(tiny, term, None, None)
+    f64 = to.InitialValueProblem(torch.zeros(3, 6, dtype=torch.float64), t0.double(), t1.double())
+    assert solver._step_fusable(f64, term, None, None)                            # 2-element vectors in fp64
+    other = to.ODETerm(lambda t, y: -y)
+    assert not solver._step_fusable(plain, other, None, None)
+    solver.use_step_fusion = False
+    assert not solver._step_fusable(plain, term, None, None)
+    assert plain_mlp_term(to.ODETerm(lambda t, y: y)) and not plain_mlp_term(to.ODETerm(lambda t, y, a: y, with_args=True))
+
+
+def test_new_entry_points_report_argument_errors_without_a_gpu():
+    import ctypes
+
+    from torchode_b200 import _cabi
+
+    lib = _cabi.lib()
+    tab, ctrl, st = _cabi.Tableau(), _cabi.Controller(), _cabi.State()
+    tab.n_stages = 7
+    assert lib.tode_heat_step(ctypes.byref(tab), ctypes.byref(ctrl), ctypes.byref(st), 1.0, None, None, None, None) == -1
+    assert lib.tode_mlp_tanh256_stage_forward(ctypes.byref(tab), 1, ctypes.byref(st), _cabi.KPtrs(), None, None, None,
+                                              None, 3, None) == -1
+    # split-mode scratch: two partials per (sample, chunk) for the initial step + the finish's records
+    B, F = 64, 1 << 20
+    chunks_f32, chunks_f64 = F // 4096, F // 2048
+    assert lib.tode_scratch_elems(B, F) >= 2 * B + 2 * B * max(chunks_f32, chunks_f64) + 8 * B
