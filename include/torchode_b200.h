@@ -309,7 +309,8 @@ int tode_heat1d_forward(const void* y, void* out, int64_t B, int64_t N, double k
                         void* stream);
 
 /* One whole loop iteration (runge_kutta.py:227-279, step_size_controllers.py:371-429 / 716-774,
- * adjoints.py:150-201) of a problem whose f is the heat field above, T == 0 (no t_eval): the six stage
+ * adjoints.py:150-234) of a problem whose f is the heat field above (t_eval rows, if any, monotone in the
+ * direction of time: cursor mode, st->not_yet == NULL): the six stage
  * combinations, the six stencil evaluations, the error estimate and the per-chunk error norms in ONE
  * pass over y and the FSAL slot (stage values never leave the SM), then the per-sample controller --
  * two launches, 4 rows of HBM traffic instead of 56.  Replaces 6 x (tode_erk_stage,
@@ -317,10 +318,11 @@ int tode_heat1d_forward(const void* y, void* out, int64_t B, int64_t N, double k
  * while sel[b] == 0 and in (y_alt, f_alt) while sel[b] == 1: a step reads one pair, writes y1 and
  * k[S-1] into the other, and accepting it toggles sel[b] (no commit copy).  sel: (B) bytes, zeroed by
  * the caller before the first iteration; y_alt, f_alt: (B,F), 16-byte aligned; F divisible by 4 (f32)
- * / 2 (f64); st->scratch as for tode_erk_finish.  st->y_eval receives the value at t_end of every step
- * that reaches t_end; a step that ends with status != SUCCESS otherwise has no end-point value: if any
- * sample fails, st->y_eval is not meaningful and the caller must re-solve through the stage-wise
- * entry points. */
+ * / 2 (f64); st->scratch as for tode_erk_finish.  st->y_eval receives the dense output of the points a
+ * step covers if it is accepted (T == 0: the value at t_end of every step that reaches t_end), written
+ * before the accept decision is known and rewritten by the step that does cover them; a step that ends
+ * with status != SUCCESS has no end-point value unless it reaches t_end: if any sample fails,
+ * st->y_eval is not meaningful and the caller must re-solve through the stage-wise entry points. */
 int tode_heat_step(const tode_tableau* tab, const tode_controller* ctrl, const tode_state* st,
                    double kappa, void* y_alt, void* f_alt, uint8_t* sel, void* stream);
 

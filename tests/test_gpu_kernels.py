@@ -377,6 +377,47 @@ def test_step_fused_heat_route_is_bit_identical_to_the_stage_wise_route(B, N, dt
     _assert_same_solution(fused, staged)
 
 
+@pytest.mark.parametrize("layout", ["rows", "broadcast", "reverse", "non-monotone"])
+@pytest.mark.parametrize("N,dtype,method", [(4100, torch.float32, "tsit5"), (2054, torch.float64, "dopri5"),
+                                            (3 * 4096 + 1024 + 4, torch.float32, "dopri5")])
+def test_step_fused_heat_route_dense_output(N, dtype, method, layout):
+    """t_eval with the step-fused kernels: the points a step covers are evaluated before its accept
+    decision is known (rows of a rejected step are rewritten) -- same bits, same n_initialized as the
+    stage-wise finish kernel; rows that are not monotone in time hand over to its scan-all mode."""
+    from torchode_b200.fields import Heat1D
+
+    B = 5
+    base = _heat_problem(B, N, dtype, dtype, seed=N, reverse=layout == "reverse")
+    g = torch.Generator().manual_seed(N + 1)
+    lo, hi = base.t_start.cpu(), base.t_end.cpu()
+    frac = torch.sort(torch.rand(B, 17, generator=g, dtype=dtype), dim=1).values
+    frac[::2, 0] = 0.0  # rows whose first point is t_start
+    frac[1, -1] = 1.0   # a row whose last point is t_end
+    t_eval = lo[:, None] + (hi - lo)[:, None] * frac
+    if layout == "broadcast":
+        problem = to.InitialValueProblem(base.y0, base.t_start, torch.full_like(base.t_end, 0.5),
+                                         torch.linspace(0, 0.5, 23, dtype=dtype, device=DEV).expand(B, -1))
+    else:
+        if layout == "non-monotone":
+            t_eval[2, [3, 9]] = t_eval[2, [9, 3]]
+        problem = to.InitialValueProblem(base.y0, base.t_start, base.t_end, t_eval.to(DEV))
+
+    def make_solver():
+        term = to.ODETerm(Heat1D(20.0))
+        step = (to.Tsit5 if method == "tsit5" else to.Dopri5)(term)
+        return to.AutoDiffAdjoint(step, to.IntegralController(1e-6, 1e-3, term=term))
+
+    (fused, run_f), (staged, run_s) = _solve_both_heat_routes(problem, make_solver)
+    if layout == "non-monotone":
+        assert run_f["route"] == "staged" and run_f["general"]
+    else:
+        assert run_f["route"] == "step-fused" and run_s["route"] == "staged"
+        assert int(fused.stats["n_steps"].sum()) > int(fused.stats["n_accepted"].sum())  # some steps were rejected
+    assert (fused.status == 0).all()
+    assert fused.stats["n_initialized"].cpu().tolist() == [problem.n_evaluation_points] * B
+    _assert_same_solution(fused, staged)
+
+
 def test_step_fused_heat_route_with_dt0_and_graph_replay():
     from torchode_b200.fields import Heat1D
 

@@ -278,7 +278,8 @@ def test_route_predicates_of_the_fused_step_and_stage_routes():
     assert not solver._step_fusable(plain, term, ("args",), None)                 # f(t, y, args)
     assert not solver._step_fusable(plain, term, None, object())                  # recorded (autograd) solve
     with_t_eval = to.InitialValueProblem(y0, t0, t1, torch.linspace(0, 1, 5).expand(3, -1))
-    assert not solver._step_fusable(with_t_eval, term, None, None)                # dense output: stage-wise kernels
+    assert solver._step_fusable(with_t_eval, term, None, None)                    # dense output in cursor mode
+    assert not solver._step_fusable(with_t_eval, term, None, None, general=True)  # scan-all mask mode: stage-wise
     ragged = to.InitialValueProblem(torch.zeros(3, 4098 + 1), t0, t1)
     assert not solver._step_fusable(ragged, term, None, None)                     # rows of whole 16-byte vectors only
     tiny = to.InitialValueProblem(torch.zeros(3, 4), t0, t1)

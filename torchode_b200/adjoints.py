@@ -245,12 +245,13 @@ class AutoDiffAdjoint(nn.Module):
     # ------------------------------------------------------------------------------------
     # route 2: stage-wise kernels around an opaque f
     # ------------------------------------------------------------------------------------
-    def _step_fusable(self, problem, term_, args, record) -> bool:
+    def _step_fusable(self, problem, term_, args, record, general: bool = False) -> bool:
         """Problems whose loop iteration ``tode_heat_step`` covers: the built-in stencil field as a plain
-        ``f(t, y)``, no dense output, rows of whole 16-byte vectors."""
+        ``f(t, y)``, rows of whole 16-byte vectors, ``t_eval`` rows (if any) monotone in the direction of
+        time (``general``: the scan-all mask mode of the stage-wise kernels)."""
         vec = 16 // problem.y0.element_size()
-        return (self.use_step_fusion and record is None and type(term_.f) is Heat1D and not term_.with_args
-                and args is None and problem.t_eval is None and problem.n_features % vec == 0
+        return (self.use_step_fusion and record is None and not general and type(term_.f) is Heat1D
+                and not term_.with_args and args is None and problem.n_features % vec == 0
                 and problem.n_features >= 2 * vec)
 
     def _solve_staged(self, problem, term_, dt0, args, general: bool = False, record=None,
@@ -259,7 +260,7 @@ class AutoDiffAdjoint(nn.Module):
         method, ctrl = self.step_method, self.step_size_controller
         dev, D, Tt = problem.device, problem.data_dtype, problem.time_dtype
         B, F, Tn = problem.batch_size, problem.n_features, problem.n_evaluation_points
-        step_fusion = step_fusion and self._step_fusable(problem, term_, args, record)
+        step_fusion = step_fusion and self._step_fusable(problem, term_, args, record, general)
         stage_fusion = (self.use_step_fusion and record is None and type(term_.f) is TanhMLP256 and plain_mlp_term(term_)
                         and args is None and D == torch.float32 and F == TanhMLP256.WIDTH
                         and term_.f.weights.device == dev)
