@@ -11,8 +11,8 @@ import torch
 import torchode_b200 as to
 from oracle import oracle as orc
 
-from helpers import (BENIGN, FIELD_IDS, METHODS, bits_equal, cabi_of, controller_of, field_of,
-                     golden_names, load_case, max_steps_of, ulps)
+from helpers import (BENIGN, FIELD_IDS, METHODS, assert_heat_matches_reference, bits_equal, cabi_of, controller_of,
+                     field_of, golden_names, heat_golden_names, load_case, max_steps_of, ulps)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -81,3 +81,23 @@ def test_fused_matches_reference_golden(name):
     tol = 4e-5 if ys.dtype == np.float32 else tol
     rel = np.abs(ys - ysr) / np.maximum(np.abs(ysr), 1e-30)
     assert np.where(valid, rel, 0).max() <= tol
+
+
+@pytest.mark.parametrize("route", ["step-fused", "staged"])
+@pytest.mark.parametrize("name", heat_golden_names())
+def test_heat_equation_routes_match_reference_golden(name, route):
+    """configs[4] in miniature against the REAL reference's stored outputs: the step-fused route
+    (tode_heat_step) and the stage-wise route around the fields.Heat1D kernel."""
+    from torchode_b200.fields import Heat1D
+
+    case = load_case(name)
+    term = to.ODETerm(Heat1D(float(case["kappa"])))
+    solver = to.AutoDiffAdjoint(METHODS[str(case["method"])](term=term), to.IntegralController(1e-6, 1e-3, term=term))
+    solver.use_step_fusion = route == "step-fused"
+    tt = lambda k: torch.from_numpy(case[k]).to(DEV) if k in case else None
+    with torch.no_grad():
+        sol = solver.solve(to.InitialValueProblem(tt("y0"), tt("t_start"), tt("t_end"), tt("t_eval")))
+    assert solver.last_run["route"] == route
+    assert_heat_matches_reference(case, sol.stats["n_steps"].cpu().tolist(), sol.stats["n_accepted"].cpu().tolist(),
+                                  sol.stats["n_f_evals"][0], sol.stats["n_initialized"].cpu().tolist(),
+                                  sol.status.cpu().tolist(), sol.ys.cpu().numpy())

@@ -17,7 +17,8 @@ from oracle import oracle as orc
 from torchode_b200 import _cabi
 from torchode_b200.tableaus import DOPRI5, TSIT5
 
-from helpers import (BENIGN, CHAOTIC, FIELD_IDS, GOLDEN, cabi_of, golden_names, load_case, ulps)
+from helpers import (BENIGN, CHAOTIC, FIELD_IDS, GOLDEN, assert_heat_matches_reference, cabi_of, golden_names,
+                     heat_golden_names, heat_numpy_field, load_case, ulps)
 
 
 def solve_oracle(case, **kw):
@@ -165,3 +166,19 @@ def test_det_pow_properties():
     assert orc.det_pow(123.0, 0.0) == 1.0 and orc.det_pow(float("nan"), -0.0) == 1.0
     assert orc.det_pow(float("inf"), -0.2) == 0.0 and np.isnan(orc.det_pow(float("nan"), 0.2))
     assert orc.det_pow(np.float32(1e-38), -0.2, np.float32) > 3e7  # subnormal floor of the error ratio
+
+
+@pytest.mark.parametrize("name", heat_golden_names())
+def test_heat_equation_free_running_matches_reference(name):
+    """configs[4] in miniature (tests/golden/make_golden_heat.py ran the real reference): the oracle's loop
+    around an opaque stencil f, with and without t_eval, fp32 and fp64, Tsit5 and Dopri5."""
+    import torchode_b200 as to
+    from oracle import driver
+
+    case = load_case(name)
+    method = {"tsit5": to.Tsit5, "dopri5": to.Dopri5}[str(case["method"])]()
+    dtype = torch.from_numpy(case["y0"][:1, :1]).dtype
+    out = driver.solve_opaque(heat_numpy_field(case), method.to_cabi(), to.IntegralController(1e-6, 1e-3).to_cabi(5, dtype),
+                              case["y0"], case["t_start"], case["t_end"], case.get("t_eval"))
+    assert_heat_matches_reference(case, out["n_steps"], out["n_accepted"], out["n_f_evals"], out["n_initialized"],
+                                  out["status"], out["ys"])
