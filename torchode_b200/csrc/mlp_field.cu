@@ -20,8 +20,13 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/torchode_b200.h"
+
+#ifndef TODE_MLP_PDL_DEFAULT
+#define TODE_MLP_PDL_DEFAULT 0
+#endif
 
 namespace tode {
 namespace mlp {
@@ -217,7 +222,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict__ weights,
                    const float* __restrict__ biases, float* __restrict__ out, long long B, int n_layers,
                    const __grid_constant__ StageIn sp) {
-  if (sp.ctl != nullptr && sp.ctl[TODE_CTL_STOP]) return;  // speculative iteration after the stop
   constexpr int kABlockBytes = kBM * 128;  // per K-block of the activation tile
   constexpr int kSmemA = smem_a_bytes(kBM);
   // 1024-byte alignment (SWIZZLE_128B atoms) is requested from the compiler / driver; no integer
@@ -265,6 +269,23 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   };
   load_weights_async(0);
+
+  // Everything above is independent of the kernel launched before this one (TMEM allocation,
+  // barrier, the first layer's weights): under programmatic dependent launch it overlaps that
+  // kernel's tail.  Its outputs -- y, k, the control block -- are only touched from here on.  The
+  // next kernel may start its own prologue right away (it waits for OUR completion the same way).
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  if (sp.ctl != nullptr && sp.ctl[TODE_CTL_STOP]) {  // speculative iteration after the stop: undo the prologue
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (warp == 0) {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
+    }
+    return;
+  }
 
   // ---- activation tile: fp32 rows of y -> bf16, swizzled K-major (rows past B are zero) ----
   constexpr int kAChunks = kBM * (kWidth / 8);  // chunks of 8 elements
@@ -434,6 +455,19 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
 namespace tode {
 namespace mlp {
 
+// programmatic dependent launch of the stage-fused evaluations; TORCHODE_B200_PDL=0 turns it off
+static bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("TORCHODE_B200_PDL");
+    return v == nullptr ? TODE_MLP_PDL_DEFAULT != 0 : (v[0] != '0');
+  }();
+  return on;
+}
+static int launch_error() {
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
 static int launch_mlp(const float* y, const void* weights_bf16, const void* biases_f32, void* out, int64_t B,
                       int32_t n_layers, const StageIn& sp, void* stream) {
   if (!y || !weights_bf16 || !biases_f32 || !out || n_layers < 1 || n_layers > 8) return TODE_EINVAL;
@@ -452,19 +486,30 @@ static int launch_mlp(const float* y, const void* weights_bf16, const void* bias
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const cudaStream_t st = static_cast<cudaStream_t>(stream);
   // 128-row tiles unless they would leave SMs idle while 64-row tiles fill more of them
-  if ((B + 127) / 128 >= sms) {
-    mlp_tanh256_kernel<128><<<(unsigned)((B + 127) / 128), kThreads, smem_bytes(128), st>>>(
-        y, static_cast<const __nv_bfloat16*>(weights_bf16), static_cast<const float*>(biases_f32),
-        static_cast<float*>(out), (long long)B, (int)n_layers, sp);
-  } else {
-    mlp_tanh256_kernel<64><<<(unsigned)((B + 63) / 64), kThreads, smem_bytes(64), st>>>(
-        y, static_cast<const __nv_bfloat16*>(weights_bf16), static_cast<const float*>(biases_f32),
-        static_cast<float*>(out), (long long)B, (int)n_layers, sp);
-  }
-  const cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? 0 : (int)e;
+  const bool big = (B + 127) / 128 >= sms;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(big ? (B + 127) / 128 : (B + 63) / 64));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes(big ? 128 : 64);
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  // stage-fused evaluations follow a kernel of the same solve in the stream: let this launch's
+  // prologue overlap that kernel's tail (the kernel waits with griddepcontrol.wait before it
+  // reads anything the predecessor wrote)
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (sp.nk > 0 && pdl_enabled()) ? 1 : 0;
+  const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(weights_bf16);
+  const float* bias = static_cast<const float*>(biases_f32);
+  float* o = static_cast<float*>(out);
+  const long long rows = (long long)B;
+  const int layers = (int)n_layers;
+  const cudaError_t e = big ? cudaLaunchKernelEx(&cfg, mlp_tanh256_kernel<128>, y, w, bias, o, rows, layers, sp)
+                            : cudaLaunchKernelEx(&cfg, mlp_tanh256_kernel<64>, y, w, bias, o, rows, layers, sp);
+  if (e != cudaSuccess) return (int)e;
+  return launch_error();
 }
 
 }  // namespace mlp
