@@ -266,7 +266,7 @@ def test_pow_tables_are_the_generators_output_and_identical_in_both_trees(tmp_pa
 
 def test_route_predicates_of_the_fused_step_and_stage_routes():
     """Which problems the step-fused (fields.Heat1D) route takes -- host logic only, no kernel runs."""
-    from torchode_b200.adjoints import plain_mlp_term
+    from torchode_b200.adjoints import plain_term_of
     from torchode_b200.fields import Heat1D
 
     term = to.ODETerm(Heat1D(25.0))
@@ -286,11 +286,15 @@ def test_route_predicates_of_the_fused_step_and_stage_routes():
     assert not solver._step_fusable(tiny, term, None, None)
     f64 = to.InitialValueProblem(torch.zeros(3, 6, dtype=torch.float64), t0.double(), t1.double())
     assert solver._step_fusable(f64, term, None, None)                            # 2-element vectors in fp64
+    class CountingTerm(to.ODETerm):  # a term with its own protocol must see every call of f
+        pass
+
+    assert not solver._step_fusable(plain, CountingTerm(Heat1D(25.0)), None, None)
     other = to.ODETerm(lambda t, y: -y)
     assert not solver._step_fusable(plain, other, None, None)
     solver.use_step_fusion = False
     assert not solver._step_fusable(plain, term, None, None)
-    assert plain_mlp_term(to.ODETerm(lambda t, y: y)) and not plain_mlp_term(to.ODETerm(lambda t, y, a: y, with_args=True))
+    assert plain_term_of(to.ODETerm(lambda t, y: y)) and not plain_term_of(to.ODETerm(lambda t, y, a: y, with_args=True))
 
 
 def test_new_entry_points_report_argument_errors_without_a_gpu():

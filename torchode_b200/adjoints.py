@@ -48,8 +48,9 @@ def _uniform_stats(term_, problem, stats: Dict[str, Any], n_f_evals: int):
         stats["n_f_evals"].fill_(n_f_evals)
 
 
-def plain_mlp_term(term_) -> bool:
-    """A plain ODETerm around f(t, y): nothing but the evaluation count depends on the calls of f."""
+def plain_term_of(term_) -> bool:
+    """A plain ODETerm around f(t, y): nothing but the evaluation count depends on the calls of f (the
+    step- and stage-fused routes evaluate the built-in field inside their kernels, not through term.vf)."""
     return type(term_) is ODETerm and not term_.with_args
 
 
@@ -251,7 +252,7 @@ class AutoDiffAdjoint(nn.Module):
         time (``general``: the scan-all mask mode of the stage-wise kernels)."""
         vec = 16 // problem.y0.element_size()
         return (self.use_step_fusion and record is None and not general and type(term_.f) is Heat1D
-                and not term_.with_args and args is None and problem.n_features % vec == 0
+                and plain_term_of(term_) and args is None and problem.n_features % vec == 0
                 and problem.n_features >= 2 * vec)
 
     def _solve_staged(self, problem, term_, dt0, args, general: bool = False, record=None,
@@ -261,7 +262,7 @@ class AutoDiffAdjoint(nn.Module):
         dev, D, Tt = problem.device, problem.data_dtype, problem.time_dtype
         B, F, Tn = problem.batch_size, problem.n_features, problem.n_evaluation_points
         step_fusion = step_fusion and self._step_fusable(problem, term_, args, record, general)
-        stage_fusion = (self.use_step_fusion and record is None and type(term_.f) is TanhMLP256 and plain_mlp_term(term_)
+        stage_fusion = (self.use_step_fusion and record is None and type(term_.f) is TanhMLP256 and plain_term_of(term_)
                         and args is None and D == torch.float32 and F == TanhMLP256.WIDTH
                         and term_.f.weights.device == dev)
         cab_t = method.to_cabi()
