@@ -17,8 +17,8 @@ from oracle import oracle as orc
 from torchode_b200 import _cabi
 from torchode_b200.tableaus import DOPRI5, TSIT5
 
-from helpers import (BENIGN, CHAOTIC, FIELD_IDS, GOLDEN, assert_heat_matches_reference, cabi_of, golden_names,
-                     heat_golden_names, heat_numpy_field, load_case, ulps)
+from helpers import (BENIGN, CHAOTIC, FIELD_IDS, GOLDEN, assert_heat_matches_reference, cabi_of, dense_golden_names,
+                     golden_names, heat_golden_names, heat_numpy_field, load_case, ulps)
 
 
 def solve_oracle(case, **kw):
@@ -180,5 +180,25 @@ def test_heat_equation_free_running_matches_reference(name):
     dtype = torch.from_numpy(case["y0"][:1, :1]).dtype
     out = driver.solve_opaque(heat_numpy_field(case), method.to_cabi(), to.IntegralController(1e-6, 1e-3).to_cabi(5, dtype),
                               case["y0"], case["t_start"], case["t_end"], case.get("t_eval"))
+    assert_heat_matches_reference(case, out["n_steps"], out["n_accepted"], out["n_f_evals"], out["n_initialized"],
+                                  out["status"], out["ys"])
+
+
+@pytest.mark.parametrize("name", dense_golden_names())
+def test_dense_linear_field_free_running_matches_reference(name):
+    """F = 16 / 100 (tests/golden/make_golden_dense.py ran the real reference on f = y A^T): pins the per-sample
+    norm over more than four features (lane groups of the canonical order), dense output, PID control and
+    samples running backwards in time -- exact statistics, ys within 1e-10 relative (fp64)."""
+    import torchode_b200 as to
+    from oracle import driver
+
+    case = load_case(name)
+    A = case["A"]
+    method = {"tsit5": to.Tsit5, "dopri5": to.Dopri5}[str(case["method"])]()
+    ctrl = (to.PIDController(1e-8, 1e-6, 0.2, 0.5, 0.0) if str(case["ctrl"]) == "pid"
+            else to.IntegralController(1e-9, 1e-7))
+    out = driver.solve_opaque(lambda t, y: y @ A.T, method.to_cabi(), ctrl.to_cabi(5, torch.float64), case["y0"],
+                              case["t_start"], case["t_end"], case.get("t_eval"))
+    assert case["y0"].dtype == np.float64
     assert_heat_matches_reference(case, out["n_steps"], out["n_accepted"], out["n_f_evals"], out["n_initialized"],
                                   out["status"], out["ys"])
