@@ -63,6 +63,10 @@ class Workload:
     def describe(self):
         raise NotImplementedError
 
+    def describe_reference(self):
+        """The workload without this repo's route: what the reference arm runs."""
+        return self.describe().split(", ROUTE: ")[0]
+
 
 class C2(Workload):
     """Van der Pol mu=10, Tsit5 + PID(1e-8,1e-8,.2,.5,0), fp64, t in [0,20], no t_eval."""
@@ -82,7 +86,7 @@ class C2(Workload):
 
     def describe(self):
         return ("configs[1]: Van der Pol mu=10, Tsit5+PID(1e-8,1e-8,0.2,0.5,0), fp64, t in [0,20], "
-                "no t_eval, fused whole-solve kernel")
+                "no t_eval, ROUTE: fused whole-solve kernel")
 
     def algorithmic_bytes(self, batch, T):
         return batch * (16 + 16 + 16 + 32)  # y0, t_start+t_end, ys, 3 int64 stats + status
@@ -106,7 +110,7 @@ class C3(Workload):
 
     def describe(self):
         return ("configs[2]: Lotka-Volterra, Dopri5+I(1e-6,1e-3), fp32, 100 t_eval points in [0,10] "
-                "(broadcast row), fused whole-solve kernel")
+                "(broadcast row), ROUTE: fused whole-solve kernel (packed fp32, persistent grid with lane refill)")
 
     def algorithmic_bytes(self, batch, T):
         return batch * (8 + 8 + T * 8 + 32)
@@ -167,7 +171,7 @@ class C4(Workload):
 
     def describe(self):
         return ("configs[3]: neural ODE, 3x256 tanh MLP field on tcgen05 (bf16 GEMM, fp32 state), Dopri5+"
-                "I(1e-6,1e-3), t in [0,10], stage-wise route with CUDA-graph replay")
+                "I(1e-6,1e-3), t in [0,10], ROUTE: stage-wise route with CUDA-graph replay")
 
     def algorithmic_bytes(self, batch, T):
         return None
@@ -215,7 +219,7 @@ class C5(Workload):
 
     def describe(self):
         return ("configs[4]: 1-D heat equation method of lines (fields.Heat1D stencil kernel as f), "
-                "Tsit5+I(1e-6,1e-3), batch 64, dim 2^20, fp32, step-fused route (tode_heat_step: one pass per iteration)")
+                "Tsit5+I(1e-6,1e-3), batch 64, dim 2^20, fp32, ROUTE: step-fused route (tode_heat_step: one pass per iteration)")
 
     def algorithmic_bytes(self, batch, T):
         return None
@@ -390,30 +394,168 @@ def cpu_threads():
     return int(lib.orc_set_threads(cpu_cores()))
 
 
+# --------------------------------------------------------------------------------------------
+# the reference itself (torchode 1.0.1, staged verbatim under baseline/_ref): CPU eager, CPU
+# torch.compile(solver.solve), and eager on the B200 -- bounded samples of the same seeded workload
+# --------------------------------------------------------------------------------------------
+REF_SAMPLE = {"c1": 2, "c2": 8192, "c3": 65536, "c4": 1024, "c5": 8}        # CPU (SURVEY.md 8(d) probes)
+REF_SAMPLE_CUDA = {"c1": 2, "c2": 65536, "c3": 1 << 20, "c4": 8192, "c5": 8}  # torchode eager on the GPU
+REF_C5_GRID = 1 << 16
+
+
+def ref_host_inputs(workload, sb):
+    if workload.name == "c5":
+        return workload.host_inputs(0, sb, n=REF_C5_GRID)
+    return workload.host_inputs(0, sb)
+
+
+def ref_sample_text(workload, sb, what):
+    extra = f" x {REF_C5_GRID} of the 2^20 grid points" if workload.name == "c5" else ""
+    return f"{sb} of {workload.batch} samples{extra} of the same seeded workload per step, {what}"
+
+
+def time_reference(name, host, device, mode, steps, warmup, budget_s=None):
+    """Times ``steps`` solves of the staged reference (after ``warmup`` untimed ones; for
+    mode="compiled" the first warm-up call contains the compilation and is reported separately).
+    Returns dict(value, ms_per_step, accepted, n_steps_mean, steps, compile_s)."""
+    from baseline import reference
+
+    solver, problem = reference.build(name, host, device)
+    solve = solver.solve
+    compile_s = None
+    is_cuda = torch.device(device).type == "cuda"
+    sync = torch.cuda.synchronize if is_cuda else (lambda: None)
+    with torch.no_grad():
+        if mode == "compiled":
+            # BASELINE.md section 3: torch.compile(solver.solve) -- torch.compile(solver).solve(...) compiles nothing
+            solve = torch.compile(solver.solve)
+            t0 = time.perf_counter()
+            solve(problem)
+            compile_s = time.perf_counter() - t0
+        times, sol = [], None
+        t_begin = time.perf_counter()
+        for i in range(warmup + steps):
+            sync()
+            t0 = time.perf_counter()
+            sol = solve(problem)
+            sync()
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            if budget_s is not None and len(times) >= 1 and time.perf_counter() - t_begin > budget_s:
+                break  # bounded leg (context numbers only; the reference arm proper runs all K steps)
+    acc = int(sol.stats["n_accepted"].sum())
+    sec = sum(times) / len(times)
+    return {"value": acc / sec, "ms_per_step": 1e3 * sec, "accepted": acc, "steps": len(times),
+            "n_steps_mean": float(sol.stats["n_steps"].float().mean()), "compile_s": compile_s,
+            "status_nonzero": int((sol.status != 0).sum())}
+
+
+def _reference_child(args, workload, out):
+    """``--ref-child MODE``: one leg of the reference arm in its own process (a compile that fails or
+    overruns its budget must not take the arm down); prints one JSON object."""
+    mode = args.ref_child
+    if mode == "compiled":
+        if os.path.exists("/usr/bin/g++"):
+            os.environ["CXX"] = "/usr/bin/g++"  # the image's default g++ wrapper (/opt/gcc/bin) lacks libgomp.spec
+        os.environ.setdefault("TORCHINDUCTOR_CACHE_DIR", os.path.join(ROOT, "baseline", "_ref", "inductor_cache"))
+    torch.set_num_threads(cpu_cores())
+    device = "cuda" if mode == "cuda" else "cpu"
+    sb = args.batch or (REF_SAMPLE_CUDA if mode == "cuda" else REF_SAMPLE)[workload.name]
+    res = time_reference(workload.name, ref_host_inputs(workload, sb), device,
+                         "compiled" if mode == "compiled" else "eager", args.steps, args.warmup,
+                         budget_s=args.ref_budget)
+    res["sample_batch"] = sb
+    res["threads"] = torch.get_num_threads()
+    out.emit(json.dumps(res))
+    return 0
+
+
+def reference_leg(workload, mode, steps, warmup, timeout_s, budget_s=None, batch=None):
+    """Runs one leg (eager / compiled / cuda) of the reference in a child process; dict or {"error": ...}."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload.name,
+           "--ref-child", mode, "--steps", str(steps), "--warmup", str(warmup)]
+    if budget_s is not None:
+        cmd += ["--ref-budget", str(budget_s)]
+    if batch is not None:
+        cmd += ["--batch", str(batch)]
+    env = dict(os.environ)
+    env.pop("OMP_NUM_THREADS", None)  # torchrun exports OMP_NUM_THREADS=1
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout_s,
+                              env=env)
+    except subprocess.TimeoutExpired:
+        return {"error": f"timed out after {timeout_s} s"}
+    if proc.returncode != 0:
+        return {"error": f"rc {proc.returncode}: {proc.stderr.strip().splitlines()[-1] if proc.stderr.strip() else ''}"}
+    try:
+        return json.loads(proc.stdout.strip().splitlines()[-1])
+    except (ValueError, IndexError):
+        return {"error": "no JSON from the child", "stdout": proc.stdout[-300:]}
+
+
 def run_reference_arm(args, workload, out):
+    """``--impl reference``: the reference's own implementation of the path on the host cores.
+    With baseline/_ref staged: torchode itself -- K timed steps of torch.compile(solver.solve) (the
+    north star's CPU path; compilation excluded) if the compile leg succeeds within its budget, else K
+    timed eager steps; the other leg and torchode eager on the B200 ride along as context.  Without
+    baseline/_ref: the oracle port (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sb = cpu_sample_size(workload)
-    threads = cpu_threads()
-    values, times = [], []
-    for i in range(args.warmup + args.steps):
-        v, t, _ = cpu_run(workload, sb)
-        if i >= args.warmup:
-            values.append(v)
-            times.append(t)
-    value = sum(values) / len(values)
-    sample = (f"{sb} of {workload.batch} samples of the same seeded workload per step, oracle port "
-              f"(plain C + OpenMP, lock-step like the reference)")
+    from baseline import reference
+
+    threads = cpu_cores()
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": workload.dtype_name,
-        "data": "synthetic", "config": {"workload": workload.describe(), "batch_per_step": sb},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": workload.dtype_name, "data": "synthetic", "gpu_launches": 0,
     }
+    if reference.available():
+        sb = REF_SAMPLE[workload.name]
+        legs = {}
+        legs["compiled"] = reference_leg(workload, "compiled", args.steps, args.warmup, timeout_s=args.ref_compile_timeout)
+        primary = "compiled" if "error" not in legs["compiled"] else "eager"
+        if primary == "eager":
+            legs["eager"] = reference_leg(workload, "eager", args.steps, args.warmup, timeout_s=1200)
+        else:
+            legs["eager"] = reference_leg(workload, "eager", min(args.steps, 3), 1, timeout_s=600, budget_s=60)
+        if "error" in legs[primary]:
+            raise SystemExit(f"reference arm failed: {legs}")
+        if torch.cuda.is_available():
+            legs["cuda_eager"] = reference_leg(workload, "cuda", min(args.steps, 3), 1, timeout_s=600, budget_s=60)
+        r = legs[primary]
+        what = ("torchode 1.0.1 (baseline/_ref, unmodified), CPU, "
+                + ("torch.compile(solver.solve), compilation excluded" if primary == "compiled" else "eager"))
+        line.update({
+            "value": r["value"], "ms_per_step": r["ms_per_step"],
+            "config": {"workload": workload.describe_reference(), "batch_per_step": sb, "threads": r["threads"],
+                       "reference_path": primary},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                             "sample": ref_sample_text(workload, sb, what)},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "reference_legs": legs,
+        })
+    else:
+        sb = cpu_sample_size(workload)
+        n_thr = cpu_threads()
+        values, times = [], []
+        for i in range(args.warmup + args.steps):
+            v, t, _ = cpu_run(workload, sb)
+            if i >= args.warmup:
+                values.append(v)
+                times.append(t)
+        value = sum(values) / len(values)
+        sample = (f"{sb} of {workload.batch} samples of the same seeded workload per step, oracle port "
+                  f"(plain C + OpenMP, lock-step like the reference); baseline/_ref is not staged")
+        line.update({
+            "value": value, "ms_per_step": 1e3 * sum(times) / len(times),
+            "config": {"workload": workload.describe(), "batch_per_step": sb},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_thr, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        })
     out.emit(json.dumps(line))
     return 0
 
@@ -539,11 +681,18 @@ def _main(out):
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the config's)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / kernel rooflines")
+    ap.add_argument("--ref-child", default=None, choices=["eager", "compiled", "cuda"],
+                    help="internal: one leg of the reference arm (own process)")
+    ap.add_argument("--ref-budget", type=float, default=None, help="internal: stop a context leg after this many s")
+    ap.add_argument("--ref-compile-timeout", type=float, default=900.0,
+                    help="reference arm: give up on torch.compile(solver.solve) after this many seconds")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     cls, batch = WORKLOADS[args.workload]
     workload = cls(args.workload, args.batch or batch)
+    if args.impl == "reference" and args.ref_child:
+        return _reference_child(args, workload, out)
     if args.impl == "reference":
         return run_reference_arm(args, workload, out)
 

@@ -40,7 +40,8 @@
 extern "C" {
 #endif
 
-#define TODE_ABI_VERSION 2
+#define TODE_ABI_VERSION 3
+#define TODE_SUMMARY_WORDS 8
 #define TODE_MAX_STAGES 7
 #define TODE_MAX_FIELD_PARAMS 8
 #define TODE_MAX_PEERS 8
@@ -190,9 +191,10 @@ typedef struct tode_solution {
   int64_t* status;        /* (B) */
   void* t_final;          /* (B) time, may be NULL */
   void* dt_final;         /* (B) time, may be NULL */
-  /* device int32[4]: [0] max n_steps over the batch (= loop iterations of the
-   * reference), [1] first iteration (1-based) at which any sample reported a
-   * status != SUCCESS or INT32_MAX, [2] non-monotone t_eval flag */
+  /* device int32[TODE_SUMMARY_WORDS] (8-byte aligned): [0] max n_steps over the batch (= loop
+   * iterations of the reference), [1] first iteration (1-based) at which any sample reported a
+   * status != SUCCESS or INT32_MAX, [2] non-monotone t_eval flag, [3] reserved, [4..5] scratch: the
+   * 64-bit work queue of the persistent dense-output kernel, [6..7] reserved (ABI 3) */
   int32_t* summary;
   /* Multi-GPU, "write the all-gather while solving" (replaces the all_gather of ys / statistics
    * that follows a sharded solve): with n_peers > 0 every result of sample b --

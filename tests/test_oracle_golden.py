@@ -18,7 +18,7 @@ from torchode_b200 import _cabi
 from torchode_b200.tableaus import DOPRI5, TSIT5
 
 from helpers import (BENIGN, CHAOTIC, FIELD_IDS, GOLDEN, assert_heat_matches_reference, cabi_of, dense_golden_names,
-                     golden_names, heat_golden_names, heat_numpy_field, load_case, ulps)
+                     golden_names, heat_golden_names, heat_numpy_field, load_case, noise_floor, ulps, ys_rel_tol)
 
 
 def solve_oracle(case, **kw):
@@ -52,10 +52,9 @@ def test_free_running_matches_reference(name):
     ys, ysr = out["ys"], case["ys"]
     valid = (np.arange(ys.shape[1])[None, :, None] < case["n_initialized"][:, None, None]) & np.isfinite(ysr)
     rel = np.abs(ys - ysr) / np.maximum(np.abs(ysr), 1e-30)
-    # north star: 1e-5 relative in fp32 (a few cases sit at 1-4e-5: accumulated 1-ulp
-    # differences of pow / norm over 30-60 steps), 1e-10 relative in fp64
-    tol = 4e-5 if ys.dtype == np.float32 else 1e-10
-    assert np.where(valid, rel, 0).max() <= tol
+    # north star: 1e-5 relative in fp32, 1e-10 in fp64; the two fp32 cases that need more are bounded by
+    # the reference's own measured one-ulp noise floor (helpers.ys_rel_tol)
+    assert np.where(valid, rel, 0).max() <= ys_rel_tol(name, ys.dtype)
 
 
 @pytest.mark.parametrize("name", CHAOTIC)
@@ -71,6 +70,44 @@ def test_free_running_chaotic_cases_batch_level(name):
     same = (out["n_steps"] == case["n_steps"]) & (out["n_accepted"] == case["n_accepted"])
     assert same.mean() >= 0.4  # far above the reference's own noise floor would be luck
     assert abs(out["n_steps"].mean() / case["n_steps"].mean() - 1) < 0.05
+
+
+def assert_c2_ys_close(ys, ysr):
+    """1e-10 relative (north star, fp64) measured against the sample's state norm; element-wise it holds for
+    >= 99.9 % of the elements and everywhere within 1e-9: where x crosses zero while |v| ~ 10 the element-wise
+    ratio of two roundings is not bounded by 1e-10 even reference-vs-reference (0.01-0.04 %
+    of the samples above 1e-10, max 5e-10)."""
+    err = np.abs(ys - ysr)
+    assert (err / np.abs(ysr).max(axis=-1, keepdims=True)).max() <= 1e-10
+    rel = err / np.maximum(np.abs(ysr), 1e-30)
+    assert (rel <= 1e-10).mean() >= 0.999 and rel.max() <= 1e-9
+
+
+def test_large_c2_matches_reference_exactly():
+    """configs[1] at 4096 samples (tests/golden/make_golden_large.py): every count exact, ys <= 1e-10 relative."""
+    case = load_case("large_c2_vdp_f64_B4096")
+    out = solve_oracle(case)
+    assert np.array_equal(out["n_steps"], case["n_steps"]) and np.array_equal(out["n_accepted"], case["n_accepted"])
+    assert np.array_equal(out["status"], case["status"]) and out["n_f_evals"] == int(case["n_f_evals"][0])
+    assert_c2_ys_close(out["ys"], case["ys"])
+
+
+def test_large_c3_mismatch_is_below_the_reference_noise_floor():
+    """configs[2] at 4096 samples, free-running: fp32 at rtol 1e-3 is chaotic, so the
+    fraction of samples whose step counts differ from the reference is compared with the fraction by which the
+    reference differs from ITSELF under a one-ulp change of f (tests/golden/noise_floor.json: 29 %)."""
+    case = load_case("large_c3_lv_f32_B4096")
+    floor = noise_floor("large_c3_lv_f32_B4096")
+    out = solve_oracle(case)
+    assert np.array_equal(out["status"], case["status"]) and np.array_equal(out["n_initialized"], case["n_initialized"])
+    same = (out["n_steps"] == case["n_steps"]) & (out["n_accepted"] == case["n_accepted"])
+    mismatch = 1 - same.mean()
+    print(f"count mismatch vs reference {mismatch:.4f}; reference vs itself {floor['count_mismatch_fraction']:.4f}")
+    assert mismatch <= floor["count_mismatch_fraction"]
+    assert abs(out["n_steps"].mean() / case["n_steps"].mean() - 1) < 0.01
+    rel = np.abs(out["ys"] - case["ys"]) / np.maximum(np.abs(case["ys"]), 1e-30)
+    per_sample = rel.reshape(rel.shape[0], -1).max(axis=1)
+    assert np.median(per_sample[same]) <= 1e-5  # the typical same-count sample meets the north star's fp32 bound
 
 
 TRACED = [n for n in golden_names() if "trace_n" in load_case(n)]
@@ -168,7 +205,7 @@ def test_det_pow_properties():
     assert orc.det_pow(np.float32(1e-38), -0.2, np.float32) > 3e7  # subnormal floor of the error ratio
 
 
-@pytest.mark.parametrize("name", heat_golden_names())
+@pytest.mark.parametrize("name", heat_golden_names() + ["large_heat_f32_tsit5_F16384", "large_heat_f32_tsit5_F65536"])
 def test_heat_equation_free_running_matches_reference(name):
     """configs[4] in miniature (tests/golden/make_golden_heat.py ran the real reference): the oracle's loop
     around an opaque stencil f, with and without t_eval, fp32 and fp64, Tsit5 and Dopri5."""

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+SUMMARY_WORDS = 8
 MAX_STAGES = 7
 MAX_FIELD_PARAMS = 8
 MAX_PEERS = 8

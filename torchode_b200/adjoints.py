@@ -205,7 +205,7 @@ class AutoDiffAdjoint(nn.Module):
             status = torch.empty(B, dtype=torch.long, device=dev)
         else:  # this rank's rows of its own gathered buffers: the kernel writes them exactly once
             ys, n_steps, n_accepted, n_init, status = peers.own_rows(B, max(Tn, 1), F, D)
-        summary = torch.empty(4, dtype=torch.int32, device=dev)
+        summary = torch.empty(_cabi.SUMMARY_WORDS, dtype=torch.int32, device=dev)
         sol = _cabi.SolutionOut()
         sol.ys, sol.n_steps, sol.n_accepted = ys.data_ptr(), n_steps.data_ptr(), n_accepted.data_ptr()
         sol.n_initialized, sol.status, sol.summary = n_init.data_ptr(), status.data_ptr(), summary.data_ptr()
@@ -226,7 +226,7 @@ class AutoDiffAdjoint(nn.Module):
 
     def _fused_finish(self, ctx: Dict[str, Any], summary_host=None) -> Optional[Solution]:
         """``summary_host``: the batch summary if the caller already copied it to the host."""
-        iters, first_fail, nonmono, _ = ctx["summary"].tolist() if summary_host is None else summary_host
+        iters, first_fail, nonmono = (ctx["summary"].tolist() if summary_host is None else summary_host)[:3]
         if nonmono:
             return None  # t_eval rows not monotone in time: the staged route has the general mode
         self.last_run = {"route": "fused", "kernel_launches": 2, "iterations": iters}

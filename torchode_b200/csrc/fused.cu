@@ -11,6 +11,10 @@ __global__ void summary_init_kernel(int* summary) {
   summary[1] = INT_MAX;
   summary[2] = 0;
   summary[3] = 0;
+  summary[4] = 0;  // [4..5]: 64-bit work queue of the persistent f2 kernel
+  summary[5] = 0;
+  summary[6] = 0;
+  summary[7] = 0;
 }
 
 // Multi-GPU epilogue (tode_solution.peer_global): one thread publishes this shard's iteration count

@@ -6,6 +6,7 @@
 
 #include "api_common.cuh"
 #include "erk_fused.cuh"
+#include "erk_fused_f2.cuh"
 
 namespace tode {
 
@@ -25,6 +26,40 @@ static int launch_fused_k(const FusedArgs<D, T>& a, cudaStream_t stream) {
   const unsigned grid = (unsigned)((a.B + kThreads - 1) / kThreads);
   solve_fused_kernel<D, T, F, FIELD, TODE_FUSED_MINB, CK, TE><<<grid, kThreads, 0, stream>>>(a);
   return launch_status();
+}
+
+// fp32 state and time, two features, t_eval rows (BASELINE configs[2]): the packed-fp32 persistent
+// kernel of erk_fused_f2.cuh -- pre-pass (initial step, monotonicity) + solve with lane refill.
+// The pre-pass lends the low words of the int64 n_steps output as its (B) float scratch.
+#ifndef TODE_F2_MINB
+#define TODE_F2_MINB 5
+#endif
+template <int FIELD, int CK>
+static int launch_fused_f2_k(const FusedArgs<float, float>& a, cudaStream_t stream) {
+  summary_init_kernel<<<1, 1, 0, stream>>>(a.summary);
+  float* dt_scratch = reinterpret_cast<float*>(a.n_steps);
+  fused_f2_init_kernel<FIELD><<<(unsigned)((a.B + 255) / 256), 256, 0, stream>>>(a, dt_scratch, 2);
+  const unsigned grid = grid_for(a.B, kF2Threads, TODE_F2_MINB);
+  solve_fused_f2_kernel<FIELD, TODE_F2_MINB, CK><<<grid, kF2Threads, 0, stream>>>(
+      a, dt_scratch, 2, reinterpret_cast<unsigned long long*>(a.summary + 4));
+  return launch_status();
+}
+template <int FIELD>
+static int launch_fused_f2(const FusedArgs<float, float>& a, int ck, cudaStream_t stream) {
+  switch (ck) {
+    case 0: return launch_fused_f2_k<FIELD, 0>(a, stream);
+    case 1: return launch_fused_f2_k<FIELD, 1>(a, stream);
+    default: return launch_fused_f2_k<FIELD, 2>(a, stream);
+  }
+}
+// does the problem fit the f2 kernel?  (ys replicas written by the kernel keep the general kernel)
+template <typename D, typename T>
+static bool f2_route(const FusedArgs<D, T>& a, long long F) {
+  if (sizeof(D) != 4 || sizeof(T) != 4 || F != 2 || a.Tn <= 0 || a.Tn > 0x3fffffff) return false;
+  if (!aligned_to(a.summary, 8) || getenv("TODE_NO_F2") != nullptr) return false;
+  for (int p = 0; p < a.n_peers; ++p)
+    if (a.p_ys[p] != nullptr) return false;
+  return true;
 }
 
 // SPEC: instantiate the specialised variants (same data / time dtype, the built-in 2-feature
@@ -93,6 +128,16 @@ int launch_fused(int field, const double* fp, const tode_tableau* tab, const tod
   // what the controller needs: 0 = no history, 1 = r1 only, 2 = r1 and r2
   const int ck = !a.ctrl.pid ? 0 : (a.ctrl.e_prev2 == 0.0 ? 1 : 2);
   constexpr bool kSame = sizeof(D) == sizeof(T);
+  if constexpr (sizeof(D) == 4 && sizeof(T) == 4) {
+    if (f2_route(a, prob->F)) {
+      switch (field) {
+        case TODE_FIELD_LINEAR: return launch_fused_f2<TODE_FIELD_LINEAR>(a, ck, stream);
+        case TODE_FIELD_VAN_DER_POL: return launch_fused_f2<TODE_FIELD_VAN_DER_POL>(a, ck, stream);
+        case TODE_FIELD_LOTKA_VOLTERRA: return launch_fused_f2<TODE_FIELD_LOTKA_VOLTERRA>(a, ck, stream);
+        default: return TODE_EINVAL;
+      }
+    }
+  }
   switch (field) {
     case TODE_FIELD_LINEAR:
       switch (prob->F) {

@@ -219,7 +219,7 @@ def solve_sharded_symmetric(solver, local_problem: InitialValueProblem, ws: Symm
         if g_replay:
             # some shard saw a failure before its last iteration: "any failure stops the batch"
             # holds per shard -- that shard replays with the cap and republishes
-            iters, first_fail, _, _ = ctx["summary"].tolist()
+            iters, first_fail = ctx["summary"].tolist()[:2]
             if first_fail != _INT32_MAX and first_fail < iters:
                 ctx["run"](first_fail)
                 ws.push_ys()

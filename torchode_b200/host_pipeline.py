@@ -15,6 +15,7 @@ from typing import Any, Dict, List, Optional
 
 import torch
 
+from . import _cabi
 from .adjoints import _INT32_MAX, AutoDiffAdjoint
 from .distributed import shard_bounds
 from .problems import InitialValueProblem
@@ -48,7 +49,7 @@ def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, devic
     else:
         ys = _pinned_like((B, max(Tn, 1), F), D)
         status, n_steps, n_accepted, n_init = (_pinned_like((B,), torch.long) for _ in range(4))
-    summaries = torch.empty((chunks, 4), dtype=torch.int32, pin_memory=True)
+    summaries = torch.empty((chunks, _cabi.SUMMARY_WORDS), dtype=torch.int32, pin_memory=True)
     te_host = problem.t_eval
     te_broadcast = te_host is not None and te_host.stride(0) == 0
 
@@ -91,7 +92,7 @@ def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, devic
             ctx = pending[i]
             sol_i = ctx.get("sol")
             if sol_i is None:
-                iters, first_fail, nonmono, _ = summaries[i].tolist()
+                iters, first_fail, nonmono = summaries[i].tolist()[:3]
                 if nonmono or (first_fail != _INT32_MAX and first_fail < iters):
                     # rare: replay after a failure / general t_eval mode -> finish this chunk in order
                     with torch.cuda.stream(streams[i]):
