@@ -325,14 +325,17 @@ def ev_pair():
 # --------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle port on the host cores, bounded sample
 # --------------------------------------------------------------------------------------------
-def cpu_run(workload, sample_batch, repeats=1):
+def cpu_run(workload, sample_batch, repeats=1, host=None, want_output=False):
+    """The oracle port on ``sample_batch`` samples (``host``: explicit inputs, e.g. the first rows of the
+    batch the GPU solved).  Returns (accepted steps / s, seconds, accepted[, oracle output])."""
     from oracle import oracle as orc
     from torchode_b200.single_step_methods import ExplicitRungeKutta  # noqa: F401
 
     if getattr(workload, "staged", False):
         return cpu_run_opaque(workload, sample_batch)
     field, method, ctrl = workload.components()
-    host = workload.host_inputs(0, sample_batch)
+    if host is None:
+        host = workload.host_inputs(0, sample_batch)
     tab = method.to_cabi()
     cc = ctrl.to_cabi(method.convergence_order(), host["y0"].dtype)
     t_eval = host["t_eval"]
@@ -350,6 +353,8 @@ def cpu_run(workload, sample_batch, repeats=1):
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     acc = int(out["n_accepted"].sum())
+    if want_output:
+        return acc / best, best, acc, out
     return acc / best, best, acc
 
 
@@ -672,72 +677,99 @@ def main():
         return _main(out)
 
 
-def _main(out):
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))  # c2 = BASELINE configs[1]
-    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the config's)")
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / kernel rooflines")
-    ap.add_argument("--ref-child", default=None, choices=["eager", "compiled", "cuda"],
-                    help="internal: one leg of the reference arm (own process)")
-    ap.add_argument("--ref-budget", type=float, default=None, help="internal: stop a context leg after this many s")
-    ap.add_argument("--ref-compile-timeout", type=float, default=900.0,
-                    help="reference arm: give up on torch.compile(solver.solve) after this many seconds")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+class Env:
+    """Process-wide context of one bench run."""
 
-    cls, batch = WORKLOADS[args.workload]
-    workload = cls(args.workload, args.batch or batch)
-    if args.impl == "reference" and args.ref_child:
-        return _reference_child(args, workload, out)
-    if args.impl == "reference":
-        return run_reference_arm(args, workload, out)
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference "
-                         "for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
-    from torchode_b200.distributed import SymmetricWorkspace, gather_solution, solve_sharded_symmetric
+            dist.init_process_group("nccl", device_id=self.device)
+            self.dist = dist
+        self.hbm_peak, self.peak_src = peaks()
+        self.l2buf = torch.zeros(128 << 20, dtype=torch.float32, device=self.device)  # 512 MiB
 
-    hbm_peak, peak_src = peaks()
-    B = workload.batch
-    host = workload.host_inputs(rank, B)
-    host_pinned = {k: (None if v is None else v.pin_memory()) for k, v in host.items()}
-    problem = make_problem(host, device)
-    T = problem.n_evaluation_points
-    if getattr(workload, "staged", False):
-        field, method, ctrl = workload.components(device)
-    else:
-        field, method, ctrl = workload.components()
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def allreduce(self, values, op):
+        t = torch.tensor(values, dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return t.tolist()
+
+
+def redraw_failing_rows(workload, solver, host, device, rank):
+    """configs[2] at its full batch: a handful of the 2^24 seeded samples (3 on rank 0) overflow fp32 in an
+    over-long early step and end with INFINITE_NORM -- in the reference too -- which aborts the WHOLE batch
+    at iteration 4 (adjoints.py:186-190).  To time a batch that completes, those rows (and only those) get
+    fresh draws from a second seeded generator.  Untimed set-up; returns the number of rows replaced."""
+    g = torch.Generator().manual_seed(4321 + rank)
+    replaced = 0
+    for _ in range(8):
+        with torch.no_grad():
+            sol = solver.solve(make_problem(host, device))
+        bad = (sol.status != 0).nonzero().flatten().cpu()
+        if bad.numel() == 0:
+            break
+        host["y0"][bad] = 1 + torch.rand(bad.numel(), 2, generator=g)
+        replaced += int(bad.numel())
+    return replaced
+
+
+def run_workload(env, name, batch, steps, warmup, *, main, extras):
+    """Times ``steps`` solves of one workload (after ``warmup`` untimed ones) on this rank's GPU -- for
+    world > 1 on this rank's slice, the step ending with the full-batch Solution on every rank.
+    ``main``: the workload of the JSON line proper (weak scaling: ``batch`` samples per GPU; e2e with host
+    buffers is measured); else a ``per_config`` entry (strong scaling of the config's batch, 3 steps)."""
+    from torchode_b200.distributed import SymmetricWorkspace, gather_solution, shard_bounds, solve_sharded_symmetric
+
+    cls, _ = WORKLOADS[name]
+    world, rank, device, dist = env.world, env.rank, env.device, env.dist
+    if main or world == 1:
+        B = batch
+        workload = cls(name, B)
+        host = workload.host_inputs(rank, B)
+        scaling = "weak"
+    else:  # strong scaling: this rank's slice of the config's batch (same seeded global inputs on every rank)
+        workload = cls(name, batch)
+        full = workload.host_inputs(0, batch)
+        lo, hi = shard_bounds(batch, rank, world)
+        assert (hi - lo) * world == batch, "per_config entries need batches divisible by the world size"
+        host = {k: (v if (v is None or (k == "t_eval" and v.ndim == 1)) else v[lo:hi].clone()) for k, v in full.items()}
+        B = hi - lo
+        scaling = "strong"
+    staged_wl = getattr(workload, "staged", False)
+    field, method, ctrl = workload.components(device) if staged_wl else workload.components()
     solver = to.AutoDiffAdjoint(method, ctrl)
     solver.use_cuda_graph = getattr(workload, "graph", False)
-    l2buf = torch.zeros(128 << 20, dtype=torch.float32, device=device)  # 512 MiB
+    redrawn = 0
+    if name == "c3":
+        redrawn = redraw_failing_rows(workload, solver, host, device, rank)
+    problem = make_problem(host, device)
+    T = problem.n_evaluation_points
+    F = int(problem.n_features)
 
-    # N > 1, fused route: the kernel writes the gathered Solution into every rank's symmetric
-    # (peer-mapped) buffers while it solves -- no all-gather after the solve; stage-wise workloads
-    # gather with NCCL
+    # N > 1, fused route: the gathered Solution is assembled in every rank's symmetric (peer-mapped)
+    # buffers while the shards solve -- statistics by the kernel's own peer stores, dense-output blocks
+    # by bulk pushes that overlap the next chunk's solve; stage-wise workloads gather with NCCL
     ws, ts_full = None, None
-    if world > 1 and not getattr(workload, "staged", False):
+    if world > 1 and not staged_wl:
         try:
-            ws = SymmetricWorkspace(B, T, int(problem.n_features), problem.data_dtype, device)
+            ws = SymmetricWorkspace(B, T, F, problem.data_dtype, device)
         except Exception as exc:  # no symmetric memory on this box: every rank falls back to NCCL
-            print(f"[rank {rank}] symmetric memory unavailable ({type(exc).__name__}: {exc}); NCCL gather",
-                  file=sys.stderr)
+            print(f"[rank {rank}] symmetric memory unavailable ({type(exc).__name__}: {exc}); NCCL gather", file=sys.stderr)
             ws = None
-        ok = torch.tensor([1 if ws is not None else 0], device=device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if not int(ok):
+        if not int(env.allreduce([1 if ws is not None else 0], "MIN")[0]):
             ws = None
     if ws is not None:
         if T == 0:
@@ -745,47 +777,52 @@ def _main(out):
             dist.all_gather_into_tensor(ts_full, problem.t_end[:, None].contiguous())
         else:
             ts_full = problem.t_eval[:1].expand(B * world, -1)  # the workloads share one t_eval row
+    n_chunks_mg = 4 if (ws is not None and T > 0) else 1
 
     def step():
         if ws is not None:
-            return solve_sharded_symmetric(solver, problem, ws, ts=ts_full)
+            return solve_sharded_symmetric(solver, problem, ws, ts=ts_full, chunks=n_chunks_mg)
         sol = solver.solve(problem)
         if world > 1:
             sol = gather_solution(sol, B * world, ts=None if T == 0 else problem.t_eval)
         return sol
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     with torch.no_grad():
-        # the clock sampler (an nvidia-smi child polling NVML) starts before the warm-up so that its
-        # start-up does not land in the first timed step; warm-up steps are shaped like timed ones
-        sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
-        for _ in range(args.warmup):
-            flush_l2(l2buf)
-            sol = step()
-        barrier()
+        sampler = ClockSampler(torch.cuda.current_device()) if (rank == 0 and main) else None
+        for _ in range(warmup):
+            flush_l2(env.l2buf)
+            step()
+        env.barrier()
         times = []
-        t_epoch = time.time()
-        t_wall = time.perf_counter()
-        for _ in range(args.steps):
-            flush_l2(l2buf)
+        t_epoch, t_wall = time.time(), time.perf_counter()
+        for _ in range(steps):
+            flush_l2(env.l2buf)
             e0, e1 = ev_pair()
             e0.record()
-            sol = step()
+            step()
             e1.record()
             e1.synchronize()
             times.append(e0.elapsed_time(e1))
-        barrier()
+        env.barrier()
         t_wall = time.perf_counter() - t_wall
         clocks = sampler.stop(since=t_epoch - 0.05) if sampler is not None else None
-        timed_route = dict(solver.last_run)  # route / launches of the timed steps
+        timed_route = dict(solver.last_run)
 
-        # per-rank accepted steps of ONE step (every step solves the same inputs)
-        local = solver.solve(problem)
+        # the shard alone (no gather), for the multi-GPU lines: what the exchange costs on top
+        solve_only_ms = None
+        if world > 1:
+            ts_ = []
+            for _ in range(3):
+                flush_l2(env.l2buf)
+                e0, e1 = ev_pair()
+                e0.record()
+                solver.solve(problem)
+                e1.record()
+                e1.synchronize()
+                ts_.append(e0.elapsed_time(e1))
+            solve_only_ms = env.allreduce([statistics.median(ts_)], "MAX")[0]
+
+        local = solver.solve(problem)  # per-rank statistics of ONE step (every step solves the same inputs)
         acc_local = int(local.stats["n_accepted"].sum())
         attempted_local = int(local.stats["n_steps"].sum())
         iters = (int(local.stats["n_f_evals"][0]) - 2) // 6
@@ -793,29 +830,76 @@ def _main(out):
         n_status = int((local.status != 0).sum())
         mean_steps = float(local.stats["n_steps"].float().mean())
 
-        total_ms = torch.tensor([sum(times)], dtype=torch.float64, device=device)
-        acc = torch.tensor([acc_local], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
-        ms_per_step = float(total_ms) / args.steps
-        value = float(acc) / (ms_per_step * 1e-3)
+        total_ms = env.allreduce([sum(times)], "MAX")[0]
+        acc = env.allreduce([acc_local], "SUM")[0]
+        ms_per_step = total_ms / steps
+        value = acc / (ms_per_step * 1e-3)
 
-        # ---- end-to-end through the public API with HOST buffers (every rank, max over ranks) ----
-        # (a) to.solve_from_host: pinned host problem in, pinned host Solution out, the batch cut into
-        #     chunks whose H2D / solve / D2H overlap on their own streams -- the call a user with host
-        #     data makes; (b) the same through three separate user-level steps (copy in, solve, copy
-        #     out), for comparison.  Both timed regions contain every byte of y0 / t_start / t_end
-        #     going in and of ys / n_steps / n_accepted / n_initialized / status coming out.
-        h2d = sum(v.numel() * v.element_size() for v in host_pinned.values() if v is not None)
-        te_h = host_pinned["t_eval"]
-        if te_h is not None and te_h.ndim == 1:
-            te_h = te_h.expand(B, -1)
-        host_problem = to.InitialValueProblem(host_pinned["y0"], host_pinned["t_start"], host_pinned["t_end"], te_h)
-        staged_wl = getattr(workload, "staged", False)
-        n_chunks = 1 if staged_wl else 8
-        e2e_times, e2e_plain, d2h, host_out, hsol = [], [], 0, None, None
-        for i in range(2 + max(3, args.steps // 2)):
+    # ---- roofline of the dominant kernel -------------------------------------------------------
+    kernel_ms = statistics.median(times) if world == 1 else (solve_only_ms or ms_per_step)
+    alg_bytes = workload.algorithmic_bytes(B, T)
+    route = last_run.get("route", "")
+    step_fused = route.startswith("step-fused")
+    e = 4 if workload.dtype_name == "f32" else 8
+    if alg_bytes is None:
+        # stage-wise workloads: solver-owned algorithmic traffic = 44 F e per attempted sample-step
+        # (the user's f is not part of it); step-fused route: y and f0 read, y1 and
+        # k6 written per attempted step (accepting a step flips a buffer selector: no commit copy)
+        alg_bytes = (4 if step_fused else 44) * F * e * attempted_local
+    fused = route.startswith("fused")
+    roofline = {
+        "kernel": ("solve_fused_f2_kernel" if (fused and name == "c3") else "solve_fused_kernel") if fused else
+                  "heat_step_kernel + finish_split_control_kernel (whole step incl. f)" if step_fused else
+                  "erk_stage_kernel x6 + erk_finish_kernel (whole staged step incl. the user's f)",
+        "bound": "hbm", "achieved": alg_bytes / kernel_ms / 1e6, "peak": env.hbm_peak, "unit": "GB/s",
+        "frac": alg_bytes / kernel_ms / 1e6 / env.hbm_peak, "traffic": None,
+        "peak_source": env.peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+    }
+    if fused:
+        roofline["note"] = ("whole solve in registers: HBM is touched only for inputs / outputs; the kernel is bound by "
+                            + ("fp64 issue (see fp64_issue)" if name == "c2" else
+                               "instruction issue (about 14 thread instructions per byte of output against a machine "
+                               "balance of 5.8; DESIGN.md section 4)")
+                            + "; the HBM-bound kernels of the stage-wise path are in roofline_kernels")
+    res = {
+        "value": value, "ms_per_step": ms_per_step, "scaling": scaling, "dtype": workload.dtype_name,
+        "config": {"workload": workload.describe(), "batch_per_gpu": B, "global_batch": B * world, "features": F,
+                   "t_eval_points": T, "loop_iterations": iters, "mean_n_steps": mean_steps,
+                   "samples_with_failure_status": n_status},
+        "roofline": roofline, "route": last_run, "steps": steps, "warmup": warmup,
+        "gpu_launches": int(last_run.get("kernel_launches", last_run.get("kernel_launches_min", 0))) * steps,
+    }
+    if name == "c3":
+        res["config"]["rows_redrawn"] = redrawn
+        res["config"]["rows_redrawn_why"] = ("samples whose solve ends in INFINITE_NORM (fp32 overflow in an over-long "
+                                             "early step, identically in the reference) abort the whole batch at "
+                                             "iteration 4; they are re-drawn (untimed set-up) so the batch completes")
+    if world > 1:
+        res["solve_only_ms"] = solve_only_ms
+        res["config"]["multi_gpu"] = (
+            ("independent batch slices; statistics by the fused kernel's peer stores (symmetric memory over NVLink), "
+             f"dense-output blocks pushed to every peer in {n_chunks_mg} chunks under the next chunk's solve, "
+             "iteration / failure counts by system-scope atomics, two signal-pad barriers per step, no collective")
+            if ws is not None else "independent batch slices, NCCL all-gather of ys / statistics after the solve")
+        if T > 0:
+            pushed = B * T * F * e * (world - 1)
+            res["exchange"] = {"bytes_sent_per_rank": pushed, "ms_on_top_of_the_solve": ms_per_step - solve_only_ms,
+                               "nvlink_gbs_per_rank_over_the_step": pushed / ms_per_step / 1e6}
+    if not main:
+        del ws
+        return res, None
+
+    # ---- end to end through the public API with HOST buffers (every rank, max over ranks) --------
+    host_pinned = {k: (None if v is None else v.pin_memory()) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host_pinned.values() if v is not None)
+    te_h = host_pinned["t_eval"]
+    if te_h is not None and te_h.ndim == 1:
+        te_h = te_h.expand(B, -1)
+    host_problem = to.InitialValueProblem(host_pinned["y0"], host_pinned["t_start"], host_pinned["t_end"], te_h)
+    n_chunks = 1 if staged_wl else 8
+    e2e_times, e2e_plain, d2h, host_out, hsol = [], [], 0, None, None
+    with torch.no_grad():
+        for i in range(2 + max(3, steps // 2)):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             hsol = to.solve_from_host(solver, host_problem, device, chunks=n_chunks, out=hsol)
@@ -824,8 +908,7 @@ def _main(out):
                 e2e_times.append(dt)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            prob_e = make_problem(host_pinned, device)
-            s = solver.solve(prob_e)
+            s = solver.solve(make_problem(host_pinned, device))
             outs = [s.ys, s.stats["n_steps"], s.stats["n_accepted"], s.stats["n_initialized"], s.status]
             if host_out is None:  # pinned result buffers, allocated once (first, untimed iteration)
                 host_out = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs]
@@ -836,119 +919,171 @@ def _main(out):
             d2h = sum(o.numel() * o.element_size() for o in host_out)
             if i >= 2:
                 e2e_plain.append(dt)
-        if n_status == 0:  # with failing samples the chunks stop separately (documented per-chunk scope)
-            assert int(hsol.stats["n_accepted"].sum()) == acc_local, "host-pipelined solve disagrees"
-        e2e_s = torch.tensor([statistics.median(e2e_times), statistics.median(e2e_plain)], dtype=torch.float64,
-                             device=device)
-        if world > 1:
-            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        e2e_value = float(acc) / float(e2e_s[0])
-        e2e_plain_value = float(acc) / float(e2e_s[1])
-
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return 0
-
-    # ---- roofline of the dominant kernel (the fused whole-solve kernel) -----------------------
-    kernel_ms = statistics.median(times) if world == 1 else ms_per_step
-    alg_bytes = workload.algorithmic_bytes(B, T)
-    step_fused = last_run.get("route", "").startswith("step-fused")
-    if alg_bytes is None:
-        # stage-wise workloads: solver-owned algorithmic traffic = 44 F e per attempted sample-step
-        # (DESIGN.md section 4); the user's f is not part of it
-        e = 4 if workload.dtype_name == "f32" else 8
-        alg_bytes = 44 * int(problem.n_features) * e * attempted_local
-        if step_fused:
-            # step-fused route (tode_heat_step): y and f0 read, y1 and k6 written per attempted step
-            # (accepting a step flips a buffer selector: no commit copy); f is inside the kernel
-            alg_bytes = int(problem.n_features) * e * 4 * attempted_local
-    roofline = {
-        "kernel": "solve_fused_kernel" if last_run.get("route", "").startswith("fused") else
-                  "heat_step_kernel + finish_split_control_kernel (whole step incl. f)"
-                  if step_fused else
-                  "erk_stage_kernel x6 + erk_finish_kernel (whole staged step incl. the user's f)",
-        "bound": "hbm", "achieved": alg_bytes / kernel_ms / 1e6,
-        "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / kernel_ms / 1e6 / hbm_peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full
-        # capture of the same workload (not measurable live); known for the default workload only
-        "traffic": NCU_DRAM_BYTES.get((workload.name, B)),
-        "traffic_source": NCU_DRAM_SOURCE.get((workload.name, B)),
-        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-        "note": ("one pass over y per loop iteration: stage values, the stencil's neighbours and the error "
-                 "estimate stay on chip (4 rows of traffic per attempted step instead of 56)"
-                 if step_fused else
-                 "whole solve in registers: HBM is touched only for inputs/outputs; for C2 the kernel is "
-                 "fp64-issue-bound, see fp64_issue; the HBM-bound kernels of the stage-wise path are in "
-                 "roofline_kernels"),
-    }
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": workload.dtype_name, "data": "synthetic",
-        "config": {"workload": workload.describe(), "batch_per_gpu": B, "global_batch": B * world,
-                   "features": int(problem.n_features), "t_eval_points": T,
-                   "l2": "512 MiB buffer rewritten between timed steps (L2 flush)",
-                   "loop_iterations": iters, "mean_n_steps": mean_steps,
-                   "samples_with_failure_status": n_status,
-                   "multi_gpu": ("independent batch slices; the fused kernel stores every result into all ranks' "
-                                 "symmetric (NVLink peer-mapped) gathered buffers and publishes its iteration count "
-                                 "with system-scope atomics, two signal-pad barriers per step, no collective"
-                                 if ws is not None else
-                                 "independent batch slices, NCCL all-gather of ys/stats after the solve")},
-        "roofline": roofline,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": float(e2e_s[0]) * 1e3,
-                "api": f"to.solve_from_host(solver, host_problem, device, chunks={n_chunks}): H2D, solve and D2H of "
-                       "the chunks overlap on their own streams",
-                "unpipelined": {"value": e2e_plain_value, "ms_per_step": float(e2e_s[1]) * 1e3,
-                                "api": "problem.to(device); solver.solve; results.to(pinned host)"}},
-        # fused: summary_init_kernel + solve_fused_kernel per step; staged: init + 7 per iteration
-        "gpu_launches": int(last_run.get("kernel_launches", last_run.get("kernel_launches_min", 0))) * args.steps,
-        "route": last_run,
-        "wall_s_timed_region": t_wall,
-        "step_ms_rank0": [round(t, 4) for t in times],
-    }
+    if n_status == 0:  # with failing samples the chunks stop separately (documented per-chunk scope)
+        assert int(hsol.stats["n_accepted"].sum()) == acc_local, "host-pipelined solve disagrees"
+    e2e_s = env.allreduce([statistics.median(e2e_times), statistics.median(e2e_plain)], "MAX")
+    res["e2e"] = {"value": acc / e2e_s[0], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                  "ms_per_step": e2e_s[0] * 1e3,
+                  "api": f"to.solve_from_host(solver, host_problem, device, chunks={n_chunks}): H2D, solve and D2H of "
+                         "the chunks overlap on their own streams",
+                  "unpipelined": {"value": acc / e2e_s[1], "ms_per_step": e2e_s[1] * 1e3,
+                                  "api": "problem.to(device); solver.solve; results.to(pinned host)"}}
+    res["wall_s_timed_region"] = t_wall
+    res["step_ms_rank0"] = [round(t, 4) for t in times]
     if clocks is not None:
-        line["clocks"] = clocks
-    if not args.no_extras and world == 1:
-        try:
-            peak_fma = measure_fp64_peak(device)  # tera-FMA/s
-            # fp64-pipe instructions (DFMA+DMUL+DADD+DSETP) per attempted sample-step of the fused
-            # Tsit5+PID Van der Pol kernel, from the ncu opcode mix (profiles/r01_ncu_fused_c2_v6.txt;
-            # 328 at the start of round 1, 251 with the branch-free scalar path, 210 with the
-            # table-driven pow)
-            ops_per_step = 210
-            achieved = attempted_local / (kernel_ms * 1e-3) * ops_per_step / 1e12
-            line["fp64_issue"] = {
-                "peak_tfma_per_s": peak_fma, "peak_source": "tode_bench_fp64_fma, measured live",
-                "fp64_pipe_instr_per_attempted_step": ops_per_step,
-                "achieved_tinstr_per_s": achieved, "frac": achieved / peak_fma,
-                "note": "only meaningful for the fp64 workload (c2); counts the lanes that carry a sample "
-                        "(a warp runs until its slowest lane is done: 92 % of the lane-steps are useful, "
-                        "the fp64 pipe itself is 71 % busy under ncu; a warp-step costs 2 N_fp64 + N_other = "
-                        "2*210 + 200 issue cycles, the kernel runs at 97 % of that)"}
-        except Exception as exc:  # measurement aid only
-            line["fp64_issue"] = {"error": str(exc)}
-        try:
-            line["roofline_kernels"] = measure_path_a_kernels(device, hbm_peak)
-        except Exception as exc:
-            line["roofline_kernels"] = {"error": str(exc)}
-        try:
-            sb = cpu_sample_size(workload)
-            threads = cpu_threads()
+        res["clocks"] = clocks
+    ctx = dict(workload=workload, host=host, local=local, solver=solver, problem=problem, kernel_ms=kernel_ms,
+               attempted_local=attempted_local, B=B)
+    return res, ctx
+
+
+def main_extras(env, line, ctx):
+    """Rank 0, N = 1: measured context for the default line (none of it inside the timed region)."""
+    workload, host, local, B = ctx["workload"], ctx["host"], ctx["local"], ctx["B"]
+    device = env.device
+    try:
+        peak_fma = measure_fp64_peak(device)  # tera-FMA/s
+        # fp64-pipe instructions (DFMA+DMUL+DADD+DSETP) per attempted sample-step of the fused Tsit5+PID Van der
+        # Pol kernel: a property of the compiled kernel, read off the ncu opcode mix of the committed capture
+        # (profiles/r01_ncu_fused_c2_v6.txt), not measured live
+        ops_per_step = 210
+        achieved = ctx["attempted_local"] / (ctx["kernel_ms"] * 1e-3) * ops_per_step / 1e12
+        line["fp64_issue"] = {
+            "peak_tfma_per_s": peak_fma, "peak_source": "tode_bench_fp64_fma, measured live",
+            "fp64_pipe_instr_per_attempted_step": ops_per_step,
+            "fp64_pipe_instr_source": "static: opcode mix of the kernel (profiles/r01_ncu_fused_c2_v6.txt)",
+            "achieved_tinstr_per_s": achieved, "frac": achieved / peak_fma,
+            "note": "only meaningful for the fp64 workload (c2)"}
+    except Exception as exc:  # measurement aid only
+        line["fp64_issue"] = {"error": str(exc)}
+    try:
+        line["roofline_kernels"] = measure_path_a_kernels(device, env.hbm_peak)
+    except Exception as exc:
+        line["roofline_kernels"] = {"error": str(exc)}
+    # ---- CPU baselines on a bounded sample of the same seeded inputs + bit-for-bit parity of the GPU result ----
+    try:
+        sb = min(cpu_sample_size(workload), B)
+        threads = cpu_threads()
+        if getattr(workload, "staged", False):
             v, t, _ = cpu_run(workload, sb)
+        else:
+            first = {k: (v if (v is None or (k == "t_eval" and v.ndim == 1)) else v[:sb].contiguous())
+                     for k, v in host.items()}
+            v, t, _, ref = cpu_run(workload, sb, host=first, want_output=True)
+            # the GPU solved these very samples (rows 0 .. sb-1 of its batch): every count and every ys bit
+            same = (np.array_equal(local.stats["n_steps"][:sb].cpu().numpy(), ref["n_steps"])
+                    and np.array_equal(local.stats["n_accepted"][:sb].cpu().numpy(), ref["n_accepted"])
+                    and np.array_equal(local.status[:sb].cpu().numpy(), ref["status"])
+                    and np.array_equal(local.ys[:sb].cpu().numpy(), ref["ys"], equal_nan=True))
+            line["parity_checked"] = sb if same else 0
+            line["parity"] = {"samples": sb, "against": "oracle port (oracle/), same seeded inputs: rows 0..n-1 of the "
+                              "timed batch", "bit_exact": bool(same),
+                              "compared": "n_steps, n_accepted, status, every bit of ys"}
+        line["cpu_baseline_port"] = {
+            "value": v, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sb} of {B} samples of the same seeded workload, oracle port (plain C + OpenMP), {t:.1f} s"}
+    except Exception as exc:
+        line["cpu_baseline_port"] = {"error": str(exc)}
+    from baseline import reference
+
+    if reference.available():
+        sb = REF_SAMPLE[workload.name]
+        leg = reference_leg(workload, "eager", 2, 1, timeout_s=300, budget_s=30)
+        if "error" not in leg:
             line["cpu_baseline"] = {
-                "value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": f"{sb} of {B} samples of the same seeded workload, oracle port (plain C + OpenMP), "
-                          f"{t:.1f} s"}
+                "value": leg["value"], "unit": UNIT, "cores": leg["threads"], "kind": "reference",
+                "sample": ref_sample_text(workload, sb, f"torchode 1.0.1 (baseline/_ref, unmodified) eager on the host "
+                                          f"cores, {leg['ms_per_step'] / 1e3:.1f} s per solve; torch.compile(solver.solve) "
+                                          "is timed by --impl reference")}
+        else:
+            line["cpu_baseline"] = dict(line.get("cpu_baseline_port", {}), reference_error=leg["error"])
+        # torchode eager on the SAME GPU, same seeded inputs (the like-for-like competitor, SURVEY.md 8(d)),
+        # and this repo's result for those samples next to it
+        sbc = min(REF_SAMPLE_CUDA[workload.name], B)
+        try:
+            first = {k: (v if (v is None or (k == "t_eval" and v.ndim == 1)) else v[:sbc].contiguous())
+                     for k, v in host.items()}
+            rc = time_reference(workload.name, first, str(device), "eager", 2, 1, budget_s=30)
+            rsolver, rproblem = reference.build(workload.name, first, str(device))
+            with torch.no_grad():
+                rsol = rsolver.solve(rproblem)
+            ns_same = (rsol.stats["n_steps"] == local.stats["n_steps"][:sbc]) & (
+                rsol.stats["n_accepted"] == local.stats["n_accepted"][:sbc])
+            err = (rsol.ys - local.ys[:sbc]).abs()
+            scale = rsol.ys.abs().amax(dim=-1, keepdim=True).clamp_min(1e-30)
+            line["reference_cuda"] = {
+                "value": rc["value"], "unit": UNIT, "ms_per_step": rc["ms_per_step"],
+                "sample": f"{sbc} of {B} samples (rows 0..n-1 of the timed batch), torchode 1.0.1 eager, device=cuda",
+                "parity_vs_this_repo": {"samples": sbc, "count_mismatches": int((~ns_same).sum()),
+                                        "ys_max_err_rel_to_state_norm": float((err / scale).max())}}
         except Exception as exc:
-            line["cpu_baseline"] = {"error": str(exc)}
-    out.emit(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+            line["reference_cuda"] = {"error": f"{type(exc).__name__}: {exc}"}
+    else:
+        line["cpu_baseline"] = dict(line.get("cpu_baseline_port", {}))
+
+
+PER_CONFIG = ("c1", "c3", "c4", "c5")
+
+
+def _main(out):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))  # c2 = BASELINE configs[1]
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the config's)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu baselines / kernel rooflines / per_config")
+    ap.add_argument("--ref-child", default=None, choices=["eager", "compiled", "cuda"],
+                    help="internal: one leg of the reference arm (own process)")
+    ap.add_argument("--ref-budget", type=float, default=None, help="internal: stop a context leg after this many s")
+    ap.add_argument("--ref-compile-timeout", type=float, default=900.0,
+                    help="reference arm: give up on torch.compile(solver.solve) after this many seconds")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    cls, batch = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        workload = cls(args.workload, args.batch or batch)
+        if args.ref_child:
+            return _reference_child(args, workload, out)
+        return run_reference_arm(args, workload, out)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference "
+                         "for the CPU arm")
+    env = Env()
+    res, ctx = run_workload(env, args.workload, args.batch or batch, args.steps, args.warmup, main=True,
+                            extras=not args.no_extras)
+    line = {"metric": METRIC, "value": res.pop("value"), "unit": UNIT, "n_gpus": env.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res.pop("ms_per_step"),
+            "higher_is_better": True, "scaling": res.pop("scaling"), "vs_baseline": None,
+            "dtype": res.pop("dtype"), "data": "synthetic"}
+    res["config"]["l2"] = "512 MiB buffer rewritten between timed steps (L2 flush)"
+    line.update(res)
+    if not args.no_extras and args.workload == "c2" and args.batch is None:
+        # the other BASELINE configs in the same run: 3 timed steps each (2 warm-up), L2 flushed between steps;
+        # N > 1: strong scaling of the config's own batch, the step ends with the full Solution on every rank
+        per = {}
+        for name in PER_CONFIG:
+            if env.world > 1 and name == "c1":
+                continue  # two samples do not shard
+            try:
+                torch.cuda.empty_cache()
+                r, _ = run_workload(env, name, WORKLOADS[name][1], 3, 2, main=False, extras=False)
+                r["metric"], r["unit"] = METRIC, UNIT
+                per[name] = r
+            except Exception as exc:  # a per_config failure must not take the default line down
+                per[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            env.barrier()
+        line["per_config"] = per
+    if env.rank == 0 and not args.no_extras and env.world == 1:
+        main_extras(env, line, ctx)
+    if env.rank == 0:
+        out.emit(json.dumps(line))
+    if env.world > 1:
+        env.dist.barrier()
+        env.dist.destroy_process_group()
     return 0
 
 

@@ -111,6 +111,11 @@ typedef struct tode_controller {
   double dt_min, dt_max;
   double almost_zero; /* 1e-38 (1e-5 for fp16), step_size_controllers.py:251-256 */
   int64_t max_steps;  /* < 0: unlimited (adjoints.py:176-181) */
+  /* stage-wise path, replay after a failure (ABI 3): > 0 = the batch is known to stop after this
+   * many loop iterations; without t_eval a sample still running then writes its end value from that
+   * iteration's interpolant, as the reference does for a batch another sample aborted
+   * (adjoints.py:298-301).  0: not a replay. */
+  int64_t iter_cap;
 } tode_controller;
 
 /* Device control block shared by all launches of one solve (int32 words).
@@ -193,7 +198,7 @@ typedef struct tode_solution {
   void* dt_final;         /* (B) time, may be NULL */
   /* device int32[TODE_SUMMARY_WORDS] (8-byte aligned): [0] max n_steps over the batch (= loop
    * iterations of the reference), [1] first iteration (1-based) at which any sample reported a
-   * status != SUCCESS or INT32_MAX, [2] non-monotone t_eval flag, [3] reserved, [4..5] scratch: the
+   * status != SUCCESS or INT32_MAX, [2] non-monotone t_eval flag, [3] number of kernels the call launched, [4..5] scratch: the
    * 64-bit work queue of the persistent dense-output kernel, [6..7] reserved (ABI 3) */
   int32_t* summary;
   /* Multi-GPU, "write the all-gather while solving" (replaces the all_gather of ys / statistics
@@ -206,11 +211,14 @@ typedef struct tode_solution {
    * caller pushes its finished ys block to the peers in bulk instead).  The four statistics
    * pointers of a replica may be NULL together (e.g. the caller's own replica when ys / n_steps /
    * ... above already point into it).  peer_global[p] = device int32[4] of
-   * replica p, zeroed before the launch on every rank: after the solve kernel a one-warp
-   * epilogue kernel either atomicMax-es this shard's iteration count into [0] of every
-   * replica, or -- if this shard needs the failure replay (summary[1] < summary[0]) -- ORs 1
-   * into [1] and leaves [0] alone until the replay (iter_cap > 0) has run.  No collective, no
-   * host synchronisation; the caller brackets the launch with two cross-GPU barriers. */
+   * replica p, zeroed on every rank before the launches of a step: after the solve kernel a
+   * one-thread epilogue kernel atomicMax-es (system scope) this launch's iteration count into [0]
+   * and, if a sample failed, INT32_MAX - (first failing iteration) into [2] of every replica --
+   * after a cross-GPU barrier every rank knows the batch-wide loop length and the batch-wide
+   * first failure, and replays its shard with iter_cap = that iteration if its samples ran past
+   * it ("any failure stops the whole batch", adjoints.py:186-190, across GPUs).  A replay launch
+   * (iter_cap > 0) publishes nothing.  No collective, no host synchronisation; the caller
+   * brackets the launches with two cross-GPU barriers. */
   int32_t n_peers;
   int32_t reserved;
   int64_t peer_row0;

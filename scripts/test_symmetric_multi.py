@@ -1,6 +1,8 @@
 """N-GPU check of the peer-store gather (run under torchrun on a GPU box): the fused kernel writing
-the gathered Solution into every rank's symmetric buffers must equal the NCCL-gathered Solution
-and the single-GPU solve of the whole batch, bit for bit; plus timings of both gathers."""
+the gathered Solution into every rank's symmetric buffers must equal the single-GPU solve of the whole
+batch bit for bit -- also when a sample of ONE shard fails ("any failure stops the whole batch" holds
+across GPUs on this path) -- and, without failures, the NCCL-gathered Solution; the dense-output block is
+pushed whole or in four chunks under the solve; plus timings."""
 import os
 import sys
 import time
@@ -30,17 +32,20 @@ def same(a, b, n_init=None):
 def check(name, solver, problem, rank, world):
     B, F, Tn = problem.batch_size, problem.n_features, problem.n_evaluation_points
     ws = SymmetricWorkspace(B // world, Tn, F, problem.data_dtype, problem.device)
-    for rep in range(2):  # twice: the workspace is reused
-        got = solve_sharded(solver, problem, workspace=ws)
+    full = solver.solve(problem)  # the whole batch on this GPU: what the reference semantics define
+    n_fail = int((full.status != 0).sum())
+    for rep, chunks in enumerate((1, 4, 1)):  # the workspace is reused; whole-block and chunked pushes
+        got = solve_sharded(solver, problem, workspace=ws, chunks=chunks)
+        ok = same(got.ys, full.ys, full.stats["n_initialized"]) and same(got.status, full.status)
+        for k in ("n_steps", "n_accepted", "n_initialized", "n_f_evals"):
+            ok = ok and got.stats[k].tolist() == full.stats[k].tolist()
+        assert ok, f"{name}: peer-store gather differs from the single-GPU solve (rank {rank}, rep {rep}, chunks {chunks})"
+    if n_fail == 0:  # the NCCL path stops a failing shard only
         ref = solve_sharded(solver, problem)
         ok = same(got.ys, ref.ys, ref.stats["n_initialized"]) and same(got.status, ref.status)
         for k in ("n_steps", "n_accepted", "n_initialized", "n_f_evals"):
             ok = ok and got.stats[k].tolist() == ref.stats[k].tolist()
-        assert ok, f"{name}: peer-store gather differs from the NCCL gather (rank {rank}, rep {rep})"
-    full = solver.solve(problem)
-    if int((full.status != 0).sum()) == 0:  # without failures sharding is invisible
-        assert same(got.ys, full.ys, full.stats["n_initialized"]) and got.stats["n_steps"].tolist() == full.stats["n_steps"].tolist()
-        assert got.stats["n_f_evals"].tolist() == full.stats["n_f_evals"].tolist()
+        assert ok, f"{name}: peer-store gather differs from the NCCL gather (rank {rank})"
     torch.cuda.synchronize()
     dist.barrier()
 
@@ -60,9 +65,10 @@ def check(name, solver, problem, rank, world):
     t_local = timed(lambda: solver.solve(local))
     t_nccl = timed(lambda: solve_sharded(solver, problem))
     t_sym = timed(lambda: solve_sharded(solver, problem, workspace=ws))
+    t_sym4 = timed(lambda: solve_sharded(solver, problem, workspace=ws, chunks=4))
     if rank == 0:
-        print(f"{name:28s} B={B} failures={int((full.status != 0).sum())}: local solve {t_local:.3f} ms, "
-              f"+NCCL gather {t_nccl:.3f} ms, peer stores {t_sym:.3f} ms", flush=True)
+        print(f"{name:28s} B={B} failures={n_fail}: local solve {t_local:.3f} ms, +NCCL gather {t_nccl:.3f} ms, "
+              f"peer stores {t_sym:.3f} ms, in 4 chunks {t_sym4:.3f} ms", flush=True)
 
 
 def main():
@@ -91,6 +97,12 @@ def main():
         y0b = y0.clone()
         y0b[-1, 0] = float("inf")
         check("lv f32 inf in last shard", solver, to.InitialValueProblem(y0b, t_eval=te), rank, world)
+        # configs[2] at 2^20 samples per rank: the dense-output block (838 MB per rank) rides under the solve
+        B = (1 << 20) * world
+        g = torch.Generator().manual_seed(1234)
+        y0 = (1 + torch.rand(B, 2, generator=g)).to(dev)
+        te = torch.linspace(0, 10, 100).to(dev).expand(B, -1)
+        check("C3 2^20 per rank", solver, to.InitialValueProblem(y0, t_eval=te), rank, world)
         B = (1 << 20) * world
         g = torch.Generator().manual_seed(1234)
         y0 = (torch.rand(B, 2, generator=g, dtype=torch.float64) * 4 - 2).to(dev)

@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_symbol():
 def test_struct_layouts_match_the_header():
     # sizes computed from the C declarations (LP64, natural alignment)
     assert ctypes.sizeof(_cabi.Tableau) == 16 + 8 * (7 + 49 + 7 + 7 + 21)
-    assert ctypes.sizeof(_cabi.Controller) == 16 + 8 * 11 + 8
+    assert ctypes.sizeof(_cabi.Controller) == 16 + 8 * 11 + 8 + 8  # + iter_cap (ABI 3)
     assert ctypes.sizeof(_cabi.State) == 3 * 8 + 8 + 3 * 8 + 8 + 16 * 8 + 8
     assert ctypes.sizeof(_cabi.Problem) == 3 * 8 + 8 + 4 * 8 + 8 + 8
     assert ctypes.sizeof(_cabi.SolutionOut) == 8 * 8 + 8 + 8 + 6 * 8 * _cabi.MAX_PEERS  # + peer replicas (ABI 2)

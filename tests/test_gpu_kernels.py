@@ -796,11 +796,11 @@ def test_fused_kernel_writes_replicas_of_the_gathered_buffers(with_t_eval):
             self.stats = [torch.full((4, G), -7, dtype=torch.long, device="cuda") for _ in range(world)]
             self.glob = [torch.zeros(4, dtype=torch.int32, device="cuda") for _ in range(world)]
 
-        def own_rows(self, b, n_points, f, dtype):  # replica `rank` is this rank's own gathered buffer
+        def own_rows(self, b, n_points, f, dtype, rows=None):  # replica `rank` is this rank's own gathered buffer
             lo, hi = rank * B, (rank + 1) * B
             return (self.ys[rank][lo:hi],) + tuple(self.stats[rank][k][lo:hi] for k in range(4))
 
-        def fill(self, sol, b, n_points, f, dtype):
+        def fill(self, sol, b, n_points, f, dtype, rows=None):
             sol.n_peers, sol.peer_row0 = world, rank * B
             for p in range(world):
                 remote = p != rank

@@ -12,7 +12,7 @@ import torchode_b200 as to
 from oracle import oracle as orc
 
 from helpers import (BENIGN, FIELD_IDS, METHODS, assert_heat_matches_reference, bits_equal, cabi_of, controller_of,
-                     field_of, golden_names, heat_golden_names, load_case, max_steps_of, ulps)
+                     field_of, golden_names, heat_golden_names, load_case, max_steps_of, noise_floor, ulps, ys_rel_tol)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -76,18 +76,55 @@ def test_fused_matches_reference_golden(name):
     assert sol.status.cpu().tolist() == case["status"].tolist()
     ys, ysr = sol.ys.cpu().numpy(), case["ys"]
     valid = (np.arange(ys.shape[1])[None, :, None] < case["n_initialized"][:, None, None]) & np.isfinite(ysr)
-    tol = 1e-5 if ys.dtype == np.float32 else 1e-10  # north star: 1e-5 rel fp32, 1e-10 rel fp64
-    # a few fp32 cases carry O(1e-5) solver tolerance noise on top; the fp32 bound is 4e-5
-    tol = 4e-5 if ys.dtype == np.float32 else tol
+    # north star: 1e-5 rel fp32, 1e-10 rel fp64; two fp32 cases are bounded by the reference's own measured
+    # one-ulp noise floor instead (helpers.ys_rel_tol, tests/golden/noise_floor.json)
+    with np.errstate(all="ignore"):
+        rel = np.abs(ys - ysr) / np.maximum(np.abs(ysr), 1e-30)
+    assert np.where(valid, rel, 0).max() <= ys_rel_tol(name, ys.dtype)
+
+
+@pytest.mark.parametrize("staged", [False, True])
+def test_large_c2_matches_reference_golden(staged):
+    """configs[1] at 4096 samples against the real reference's stored run (tests/golden/make_golden_large.py):
+    every count exact; ys 1e-10 relative to the sample's state norm (and element-wise for >= 99.9 %)."""
+    case = load_case("large_c2_vdp_f64_B4096")
+    sol = solve_gpu(case, staged=staged)
+    assert np.array_equal(sol.stats["n_steps"].cpu().numpy(), case["n_steps"])
+    assert np.array_equal(sol.stats["n_accepted"].cpu().numpy(), case["n_accepted"])
+    assert sol.stats["n_f_evals"].tolist() == case["n_f_evals"].tolist()
+    assert np.array_equal(sol.status.cpu().numpy(), case["status"])
+    ys, ysr = sol.ys.cpu().numpy(), case["ys"]
+    err = np.abs(ys - ysr)
+    assert (err / np.abs(ysr).max(axis=-1, keepdims=True)).max() <= 1e-10
+    rel = err / np.maximum(np.abs(ysr), 1e-30)
+    assert (rel <= 1e-10).mean() >= 0.999 and rel.max() <= 1e-9
+
+
+@pytest.mark.parametrize("staged", [False, True])
+def test_large_c3_mismatch_is_below_the_reference_noise_floor(staged):
+    """configs[2] at 4096 samples, free-running (fp32, rtol 1e-3: chaotic): the fraction of samples whose step
+    counts differ from the reference's stored run must not exceed the fraction by which the reference differs
+    from itself under a one-ulp change of f (29 %, tests/golden/noise_floor.json)."""
+    case = load_case("large_c3_lv_f32_B4096")
+    floor = noise_floor("large_c3_lv_f32_B4096")
+    sol = solve_gpu(case, staged=staged)
+    ns, na = sol.stats["n_steps"].cpu().numpy(), sol.stats["n_accepted"].cpu().numpy()
+    assert np.array_equal(sol.status.cpu().numpy(), case["status"])
+    assert np.array_equal(sol.stats["n_initialized"].cpu().numpy(), case["n_initialized"])
+    same = (ns == case["n_steps"]) & (na == case["n_accepted"])
+    print(f"count mismatch vs reference {1 - same.mean():.4f}; reference vs itself {floor['count_mismatch_fraction']:.4f}")
+    assert 1 - same.mean() <= floor["count_mismatch_fraction"]
+    ys, ysr = sol.ys.cpu().numpy(), case["ys"]
     rel = np.abs(ys - ysr) / np.maximum(np.abs(ysr), 1e-30)
-    assert np.where(valid, rel, 0).max() <= tol
+    assert np.median(rel.reshape(rel.shape[0], -1).max(axis=1)[same]) <= 1e-5
 
 
 @pytest.mark.parametrize("route", ["step-fused", "staged"])
-@pytest.mark.parametrize("name", heat_golden_names())
+@pytest.mark.parametrize("name", heat_golden_names() + ["large_heat_f32_tsit5_F16384", "large_heat_f32_tsit5_F65536"])
 def test_heat_equation_routes_match_reference_golden(name, route):
     """configs[4] in miniature against the REAL reference's stored outputs: the step-fused route
-    (tode_heat_step) and the stage-wise route around the fields.Heat1D kernel."""
+    (tode_heat_step) and the stage-wise route around the fields.Heat1D kernel.  The large_* rows (4096 / 16384
+    16-byte vectors, B = 4) take the split-mode initial step / finish and many heat_step chunks per row."""
     from torchode_b200.fields import Heat1D
 
     case = load_case(name)

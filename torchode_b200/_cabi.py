@@ -62,6 +62,7 @@ class Controller(C.Structure):
         ("dt_max", C.c_double),
         ("almost_zero", C.c_double),
         ("max_steps", C.c_int64),
+        ("iter_cap", C.c_int64),
     ]
 
 

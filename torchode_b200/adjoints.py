@@ -27,7 +27,7 @@ from .fields import BuiltinField, Heat1D, TanhMLP256
 from .problems import InitialValueProblem
 from .single_step_methods import Dopri5, SingleStepMethod, Tsit5
 from .solution import Solution
-from .step_size_controllers import IntegralController, PIDController, StepSizeController
+from .step_size_controllers import FixedStepController, IntegralController, PIDController, StepSizeController
 from .terms import ODETerm
 
 _INT32_MAX = 2**31 - 1
@@ -115,6 +115,7 @@ class AutoDiffAdjoint(nn.Module):
         else:
             term_ = term
         if not self._kernel_route():
+            self._refuse_silent_gradients(problem, term_, args)
             return self._solve_generic(problem, term, term_, dt0, args)
         if torch.compiler.is_compiling() and term is None and args is None:
             # inside torch.compile: one opaque operator with a fake kernel (compile_ops.py)
@@ -123,14 +124,16 @@ class AutoDiffAdjoint(nn.Module):
             return solve_compiled(self, problem, dt0)
 
         _launch.require_cuda(problem.y0, problem.t_start, problem.t_end, problem.t_eval, dt0)
-        if torch.is_grad_enabled() and (
-                problem.y0.requires_grad or any(p.requires_grad for p in term_.parameters())):
-            # forward = the CUDA loop (recorded), backward = recompute-based (autodiff.py)
-            if problem.batch_size == 0:
-                return self._empty_solution(problem, term_)
-            from .autodiff import solve_with_grad
+        if torch.is_grad_enabled() and problem.batch_size > 0:
+            from .autodiff import grad_leaves, solve_with_grad
 
-            return solve_with_grad(self, problem, term_, dt0, args)
+            # everything the solution depends on differentiably: y0, the term's parameters, and whatever else
+            # one evaluation of f reaches -- a model captured by a closure, tensors inside ``args``
+            leaves = grad_leaves(term_, problem, args)
+            if problem.y0.requires_grad or leaves:
+                # forward = the CUDA loop (recorded), backward = recompute-based (autodiff.py)
+                with torch.cuda.device(problem.device):
+                    return solve_with_grad(self, problem, term_, dt0, args, leaves)
         if problem.batch_size == 0:
             return self._empty_solution(problem, term_)
         with torch.no_grad(), torch.cuda.device(problem.device):
@@ -140,6 +143,27 @@ class AutoDiffAdjoint(nn.Module):
                 if sol is not None:
                     return sol
             return self._solve_staged(problem, term_, dt0, args)
+
+    def _refuse_silent_gradients(self, problem, term_, args):
+        """The generic route drives kernel-backed protocol ops (``Dopri5.step``, ``Heun.step``,
+        ``IntegralController.adapt_step_size``, the built-in interpolants ...) whose outputs carry no
+        ``grad_fn``: back-propagating through such a solve would silently yield zero / wrong gradients
+        where the reference differentiates its eager loop.  Refuse instead."""
+        if not torch.is_grad_enabled() or not problem.y0.is_cuda:
+            return
+        from .autodiff import grad_leaves
+        from .single_step_methods import Euler, ExplicitRungeKutta
+
+        kernel_backed = (isinstance(self.step_method, (ExplicitRungeKutta, Euler))
+                         or isinstance(self.step_size_controller, (IntegralController, PIDController,
+                                                                   FixedStepController)))
+        if kernel_backed and (problem.y0.requires_grad or grad_leaves(term_, problem, args)):
+            raise NotImplementedError(
+                "gradients through this solver configuration are not implemented: the solve would run on the "
+                "generic route, whose built-in components are forward-only CUDA kernels (gradients are "
+                "available for Dopri5 / Tsit5 with IntegralController / PIDController and the rms / max norm, "
+                "and through BacksolveAdjoint / JointBacksolveAdjoint); wrap the solve in torch.no_grad() "
+                "if no gradient is needed")
 
     @staticmethod
     def _empty_solution(problem, term_) -> Solution:
@@ -167,13 +191,14 @@ class AutoDiffAdjoint(nn.Module):
             return f
         return None
 
-    def _fused_launch(self, problem, term_, field: BuiltinField, dt0, peers=None) -> Dict[str, Any]:
+    def _fused_launch(self, problem, term_, field: BuiltinField, dt0, peers=None, rows=None) -> Dict[str, Any]:
         """Allocate the outputs and enqueue the fused kernel on the current stream -- no host
         synchronisation.  ``_fused_finish`` reads the batch summary (the one sync of the solve).
 
         ``peers``: a ``distributed.SymmetricWorkspace`` -- the kernel then also stores every result
         into each rank's gathered buffers (peer memory over NVLink) and publishes the iteration
-        count to every rank (``tode_solution.peer_*``)."""
+        count to every rank (``tode_solution.peer_*``); ``rows``: the row block ``[a, b)`` of this rank's
+        shard the problem is (default: the whole shard)."""
         lib = _cabi.lib()
         method, ctrl = self.step_method, self.step_size_controller
         dev, D, Tt = problem.device, problem.data_dtype, problem.time_dtype
@@ -204,14 +229,14 @@ class AutoDiffAdjoint(nn.Module):
             n_init = torch.empty(B, dtype=torch.long, device=dev)
             status = torch.empty(B, dtype=torch.long, device=dev)
         else:  # this rank's rows of its own gathered buffers: the kernel writes them exactly once
-            ys, n_steps, n_accepted, n_init, status = peers.own_rows(B, max(Tn, 1), F, D)
+            ys, n_steps, n_accepted, n_init, status = peers.own_rows(B, max(Tn, 1), F, D, rows)
         summary = torch.empty(_cabi.SUMMARY_WORDS, dtype=torch.int32, device=dev)
         sol = _cabi.SolutionOut()
         sol.ys, sol.n_steps, sol.n_accepted = ys.data_ptr(), n_steps.data_ptr(), n_accepted.data_ptr()
         sol.n_initialized, sol.status, sol.summary = n_init.data_ptr(), status.data_ptr(), summary.data_ptr()
         fp = (C.c_double * _cabi.MAX_FIELD_PARAMS)(*field.params())
         if peers is not None:
-            peers.fill(sol, B, max(Tn, 1), F, D)
+            peers.fill(sol, B, max(Tn, 1), F, D, rows)
 
         def run(cap: int):
             _cabi.check(lib.tode_solve_fused(field.field_id, fp, C.byref(cab_t), C.byref(cab_c),
@@ -226,16 +251,16 @@ class AutoDiffAdjoint(nn.Module):
 
     def _fused_finish(self, ctx: Dict[str, Any], summary_host=None) -> Optional[Solution]:
         """``summary_host``: the batch summary if the caller already copied it to the host."""
-        iters, first_fail, nonmono = (ctx["summary"].tolist() if summary_host is None else summary_host)[:3]
+        iters, first_fail, nonmono, launches = (ctx["summary"].tolist() if summary_host is None else summary_host)[:4]
         if nonmono:
             return None  # t_eval rows not monotone in time: the staged route has the general mode
-        self.last_run = {"route": "fused", "kernel_launches": 2, "iterations": iters}
+        self.last_run = {"route": "fused", "kernel_launches": launches, "iterations": iters}
         if first_fail != _INT32_MAX and first_fail < iters:
             # a failure stops the WHOLE batch at that iteration (adjoints.py:186-190): replay
             # with every sample limited to the iterations the reference would have executed
             ctx["run"](first_fail)
             iters = ctx["summary"].tolist()[0]
-            self.last_run = {"route": "fused+replay", "kernel_launches": 4, "iterations": iters}
+            self.last_run = {"route": "fused+replay", "kernel_launches": 2 * launches, "iterations": iters}
         problem = ctx["problem"]
         stats: Dict[str, Any] = {}
         _uniform_stats(ctx["term"], problem, stats, ctx["n_init_evals"] + ctx["n_stage_evals"] * iters)
@@ -256,7 +281,7 @@ class AutoDiffAdjoint(nn.Module):
                 and problem.n_features >= 2 * vec)
 
     def _solve_staged(self, problem, term_, dt0, args, general: bool = False, record=None,
-                      step_fusion: bool = True) -> Solution:
+                      step_fusion: bool = True, iter_cap: int = 0) -> Solution:
         lib = _cabi.lib()
         method, ctrl = self.step_method, self.step_size_controller
         dev, D, Tt = problem.device, problem.data_dtype, problem.time_dtype
@@ -267,6 +292,7 @@ class AutoDiffAdjoint(nn.Module):
                         and term_.f.weights.device == dev)
         cab_t = method.to_cabi()
         cab_c = ctrl.to_cabi(method.convergence_order(), D, self.max_steps)
+        cab_c.iter_cap = int(iter_cap)
         S = cab_t.n_stages
         plan = None
         if self.use_cuda_graph and record is None:
@@ -277,10 +303,13 @@ class AutoDiffAdjoint(nn.Module):
             if plan is None:
                 if len(self._plans) >= 4:
                     self._plans.clear()
+                # the plan keeps f and args alive: their ids are part of the key, and an id may be reused
+                # by another object once the original is collected
                 plan = {"st": _launch.StagedState(problem, S, bool(cab_c.pid), general=general, persistent=True),
-                        "graph": None, "kp": None, "ks": None}
+                        "graph": None, "kp": None, "ks": None, "f": term_.f, "args": args}
                 self._plans[key] = plan
             else:
+                assert plan["f"] is term_.f and plan["args"] is args
                 plan["st"].rebind(problem)
             st = plan["st"]
         else:
@@ -411,7 +440,8 @@ class AutoDiffAdjoint(nn.Module):
                     # t_eval rows are not monotone in time: redo with the scan-all mask
                     if record is not None:
                         record.snaps.clear()
-                    return self._solve_staged(problem, term_, dt0, args, general=True, record=record)
+                    return self._solve_staged(problem, term_, dt0, args, general=True, record=record,
+                                              iter_cap=iter_cap)
                 if ctl_host[_cabi.CTL_STOP]:
                     break
         torch.cuda.current_stream(dev).synchronize()
@@ -423,6 +453,15 @@ class AutoDiffAdjoint(nn.Module):
             # the step-fused kernels compute what an all-successful solve needs (no end-point value
             # for a step that fails without reaching t_end): redo on the stage-wise kernels
             return self._solve_staged(problem, term_, dt0, args, general=general, record=record, step_fusion=False)
+        if Tn == 0 and iter_cap == 0 and bool((st.status != 0).any()) and bool(st.running.any()):
+            # a failure aborted the batch while other samples were still running: the reference returns, for
+            # those, the interpolant of this last iteration evaluated at t_end (adjoints.py:298-301).  The
+            # finish kernel writes an end value only for a sample that finishes or fails itself -- unless it
+            # knows the batch's last iteration: replay with that iteration as the cap (rare path).
+            if record is not None:
+                record.snaps.clear()
+            return self._solve_staged(problem, term_, dt0, args, general=general, record=record,
+                                      step_fusion=False, iter_cap=iters)
         route = "step-fused" if step_fusion else ("stage-fused" if stage_fusion else "staged")
         self.last_run = {"route": route + "+graph" if graph is not None else route, "iterations": iters,
                          "general": general,

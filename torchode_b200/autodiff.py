@@ -60,7 +60,7 @@ def _eval_quartic(co, x):
 
 class _ReplaySolve(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, solver, term_, problem, dt0, args, y0, *params):
+    def forward(ctx, solver, term_, problem, dt0, args, n_params, y0, *params):
         rec = _Record()
         with torch.no_grad():
             detached = InitialValueProblem(y0.detach(), problem.t_start, problem.t_end, problem.t_eval)
@@ -69,6 +69,7 @@ class _ReplaySolve(torch.autograd.Function):
             raise NotImplementedError("gradients with t_eval rows that are not monotone in time")
         ctx.solver, ctx.term, ctx.problem, ctx.dt0, ctx.args, ctx.rec = solver, term_, problem, dt0, args, rec
         ctx.n_iters = solver.last_run["iterations"]
+        ctx.params = list(params[:n_params])
         ctx.save_for_backward(y0)
         solver._last_solution = sol
         ctx.mark_non_differentiable(sol.status)
@@ -78,7 +79,7 @@ class _ReplaySolve(torch.autograd.Function):
     def backward(ctx, g_ys, _g_status):
         solver, term_, problem, rec, args = ctx.solver, ctx.term, ctx.problem, ctx.rec, ctx.args
         (y0,) = ctx.saved_tensors
-        params = [p for p in term_.parameters() if p.requires_grad]
+        params = ctx.params
         method, ctrl = solver.step_method, solver.step_size_controller
         diff_dt = solver.backprop_through_step_size_control
         D, Tt, dev = problem.data_dtype, problem.time_dtype, problem.device
@@ -223,12 +224,41 @@ class _ReplaySolve(torch.autograd.Function):
         if Tn > 0:  # evaluation exactly at t_start copies y0 (adjoints.py:123-126)
             at_start = t_eval[:, 0] == t_start
             g_y0 = g_y0 + torch.where(at_start[:, None], g_ys[:, 0], torch.zeros_like(g_ys[:, 0]))
-        return (None, None, None, None, None, g_y0, *a_params)
+        return (None, None, None, None, None, None, g_y0, *a_params)
 
 
-def solve_with_grad(solver, problem: InitialValueProblem, term_, dt0, args) -> Solution:
-    """``AutoDiffAdjoint.solve`` for inputs / parameters that require gradients."""
-    params = [p for p in term_.parameters() if p.requires_grad]
-    ys, status = _ReplaySolve.apply(solver, term_, problem, dt0, args, problem.y0, *params)
+def grad_leaves(term_, problem: InitialValueProblem, args) -> List[torch.Tensor]:
+    """Every leaf tensor requiring grad that ONE evaluation of the vector field reaches, other than the
+    state itself: the term's parameters, a model captured by a closure (``ODETerm(lambda t, y: net(y))``),
+    tensors inside ``args`` (the reference differentiates all of them through its eager loop).  Found by
+    tracing f once under ``enable_grad`` and walking the autograd graph (one extra f evaluation)."""
+    from .fields import BuiltinField
+
+    if isinstance(term_.f, BuiltinField) and args is None:
+        return []  # analytic fields: plain floats, nothing to differentiate but y0
+    stats: Dict[str, Any] = {}
+    term_.init(problem, stats)
+    with torch.enable_grad():
+        y = problem.y0.detach().clone().requires_grad_()
+        out = term_.vf(problem.t_start, y, stats, args)
+    leaves, seen, stack = [], set(), [out.grad_fn]
+    while stack:
+        node = stack.pop()
+        if node is None or node in seen:
+            continue
+        seen.add(node)
+        v = getattr(node, "variable", None)
+        if v is not None and v is not y and v.requires_grad and all(v is not w for w in leaves):
+            leaves.append(v)
+        stack.extend(fn for fn, _ in node.next_functions)
+    return leaves
+
+
+def solve_with_grad(solver, problem: InitialValueProblem, term_, dt0, args,
+                    leaves: Optional[List[torch.Tensor]] = None) -> Solution:
+    """``AutoDiffAdjoint.solve`` for inputs / parameters that require gradients.  ``leaves``: what f
+    depends on differentiably besides the state (``grad_leaves``)."""
+    params = grad_leaves(term_, problem, args) if leaves is None else leaves
+    ys, status = _ReplaySolve.apply(solver, term_, problem, dt0, args, len(params), problem.y0, *params)
     ts = problem.t_eval if problem.t_eval is not None else problem.t_end[:, None]
     return Solution(ts=ts, ys=ys, stats=solver._last_solution.stats, status=status)

@@ -48,6 +48,7 @@ inline CtrlP<D, T> make_ctrl(const tode_controller* c) {
   p.dt_min = (T)c->dt_min;
   p.dt_max = (T)c->dt_max;
   p.max_steps = c->max_steps;
+  p.iter_cap = c->iter_cap;
   p.norm = c->norm;
   p.pid = c->pid;
   p.has_dt_min = c->has_dt_min;

@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(kBlock) finish_split_control_kernel(const __gr
         a.t0 = t0;
         a.dt = dt;
         if (A.Tn == 0) {
-          if (!d.running_new || d.status != TODE_SUCCESS) a.flags |= 4;
+          if (!d.running_new || d.status != TODE_SUCCESS || (c.iter_cap > 0 && (long long)ns >= c.iter_cap))
+            a.flags |= 4;
         } else {
           const T* tev = A.t_eval + b * A.te_stride;
           cur = A.cursor[b];

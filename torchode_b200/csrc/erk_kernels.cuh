@@ -457,7 +457,9 @@ __global__ void __launch_bounds__(kBlock, finish_min_blocks<D, G, VEC>()) erk_fi
     if (act) {
       if (A.Tn == 0) {
         // last effective step of this sample: it finishes or reports a failure
-        if (!running_new || status != TODE_SUCCESS) eval_point(te, A.y_eval + row);
+        // ... or the batch is known to stop here (replay after another sample's failure, adjoints.py:298-301)
+        if (!running_new || status != TODE_SUCCESS || (c.iter_cap > 0 && (long long)ns >= c.iter_cap))
+          eval_point(te, A.y_eval + row);
       } else {
         const T* tev = A.t_eval + b * A.te_stride;
         if (A.not_yet == nullptr) {

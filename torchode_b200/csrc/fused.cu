@@ -6,31 +6,31 @@
 
 namespace tode {
 
-__global__ void summary_init_kernel(int* summary) {
+__global__ void summary_init_kernel(int* summary, int n_launches) {
   summary[0] = 0;
   summary[1] = INT_MAX;
   summary[2] = 0;
-  summary[3] = 0;
+  summary[3] = n_launches;  // kernels this tode_solve_fused call launches (incl. this one)
   summary[4] = 0;  // [4..5]: 64-bit work queue of the persistent f2 kernel
   summary[5] = 0;
   summary[6] = 0;
   summary[7] = 0;
 }
 
-// Multi-GPU epilogue (tode_solution.peer_global): one thread publishes this shard's iteration count
-// -- or its need for the failure replay -- to every replica with system-scope atomics.
+// Multi-GPU epilogue (tode_solution.peer_global): one thread publishes this launch's iteration count and
+// its first failing iteration to every replica with system-scope atomics (replicas are zeroed before the
+// launches of a step, so both travel as maxima: [0] = max iterations, [2] = max (INT_MAX - first failure)).
+// A replay launch (iter_cap > 0) publishes nothing: the caller already knows the batch-wide cap.
 struct PeerGlobals {
   int n;
   int* g[TODE_MAX_PEERS];
 };
 __global__ void peer_epilogue_kernel(const int* summary, PeerGlobals pg, int after_replay) {
+  if (after_replay) return;
   const int iters = summary[0], first_fail = summary[1];
-  const bool need_replay = !after_replay && first_fail != INT_MAX && first_fail < iters;
   for (int p = 0; p < pg.n; ++p) {
-    if (need_replay)
-      atomicOr_system(pg.g[p] + 1, 1);
-    else
-      atomicMax_system(pg.g[p] + 0, iters);
+    atomicMax_system(pg.g[p] + 0, iters);
+    if (first_fail != INT_MAX) atomicMax_system(pg.g[p] + 2, INT_MAX - first_fail);
   }
   __threadfence_system();
 }

@@ -17,12 +17,12 @@ namespace tode {
 #define TODE_FUSED_MINB (sizeof(D) == 8 ? 5 : 4)
 #endif
 
-__global__ void summary_init_kernel(int* summary);
+__global__ void summary_init_kernel(int* summary, int n_launches);
 
 template <typename D, typename T, int F, int FIELD, int CK, bool TE>
 static int launch_fused_k(const FusedArgs<D, T>& a, cudaStream_t stream) {
   constexpr int kThreads = kFusedThreads;
-  summary_init_kernel<<<1, 1, 0, stream>>>(a.summary);
+  summary_init_kernel<<<1, 1, 0, stream>>>(a.summary, 2 + (a.n_peers > 0 ? 1 : 0));
   const unsigned grid = (unsigned)((a.B + kThreads - 1) / kThreads);
   solve_fused_kernel<D, T, F, FIELD, TODE_FUSED_MINB, CK, TE><<<grid, kThreads, 0, stream>>>(a);
   return launch_status();
@@ -32,14 +32,19 @@ static int launch_fused_k(const FusedArgs<D, T>& a, cudaStream_t stream) {
 // kernel of erk_fused_f2.cuh -- pre-pass (initial step, monotonicity) + solve with lane refill.
 // The pre-pass lends the low words of the int64 n_steps output as its (B) float scratch.
 #ifndef TODE_F2_MINB
-#define TODE_F2_MINB 5
+#define TODE_F2_MINB 4
 #endif
 template <int FIELD, int CK>
 static int launch_fused_f2_k(const FusedArgs<float, float>& a, cudaStream_t stream) {
-  summary_init_kernel<<<1, 1, 0, stream>>>(a.summary);
+  summary_init_kernel<<<1, 1, 0, stream>>>(a.summary, 3 + (a.n_peers > 0 ? 1 : 0));
   float* dt_scratch = reinterpret_cast<float*>(a.n_steps);
   fused_f2_init_kernel<FIELD><<<(unsigned)((a.B + 255) / 256), 256, 0, stream>>>(a, dt_scratch, 2);
-  const unsigned grid = grid_for(a.B, kF2Threads, TODE_F2_MINB);
+  int ctas_per_sm = TODE_F2_MINB;
+  if (const char* e = getenv("TODE_F2_CTAS")) {  // tuning knob: resident CTAs per SM the grid is sized for
+    const int v = atoi(e);
+    if (v >= 1 && v <= TODE_F2_MINB) ctas_per_sm = v;
+  }
+  const unsigned grid = grid_for(a.B, kF2Threads, ctas_per_sm);
   solve_fused_f2_kernel<FIELD, TODE_F2_MINB, CK><<<grid, kF2Threads, 0, stream>>>(
       a, dt_scratch, 2, reinterpret_cast<unsigned long long*>(a.summary + 4));
   return launch_status();

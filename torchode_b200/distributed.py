@@ -10,9 +10,11 @@ the CPU tests):
 * ``all_reduce(MAX)`` of the per-rank loop iteration count, because the reference's
   ``n_f_evals`` is batch-uniform (``n_init + 6 * max_b n_steps``, terms.py:54-58).
 
-Known difference to a single-device solve: "any failure stops the whole batch"
-(adjoints.py:186-190) holds per shard, not across shards (a failing sample only cuts off the
-samples of its own rank).
+"Any failure stops the whole batch" (adjoints.py:186-190) across shards: on the fused route
+(``solve_sharded_symmetric``) every shard publishes its first failing iteration with a system-scope
+atomic and every shard whose samples ran past the batch-wide first failure replays with that cap --
+the gathered Solution equals the single-device one.  On the NCCL path (``solve_sharded``, opaque
+vector fields) it holds per shard (a failing sample only cuts off the samples of its own rank).
 """
 from typing import Optional, Tuple
 
@@ -157,11 +159,14 @@ class SymmetricWorkspace:
         """Cross-GPU barrier on the current stream (signal pads of the symmetric allocation)."""
         self.hdl.barrier()
 
-    def push_ys(self):
-        """Bulk copy of this rank's ys block into every peer's gathered buffer (after the solve kernel
-        on the current stream; the current stream waits for the copies)."""
+    def push_ys(self, rows=None):
+        """Bulk copy of rows ``[a, b)`` (default: all) of this rank's ys block into every peer's gathered
+        buffer, one device-to-device copy per peer on that peer's push stream, ordered after what is on
+        the current stream now.  The current stream does NOT wait: the next chunk's solve overlaps the
+        copies; ``wait_pushes`` joins them."""
         if not self.bulk_ys:
             return
+        a, b = (0, self.local_batch) if rows is None else rows
         cur = torch.cuda.current_stream(self.buf.device)
         ready = torch.cuda.Event()
         ready.record(cur)
@@ -169,25 +174,39 @@ class SymmetricWorkspace:
         for stream, dst in zip(self._push_streams, peers):
             stream.wait_event(ready)
             with torch.cuda.stream(stream):
-                dst.copy_(self._ys_local, non_blocking=True)
+                dst[a:b].copy_(self._ys_local[a:b], non_blocking=True)
+
+    def wait_pushes(self):
+        """The current stream waits for every bulk copy enqueued by ``push_ys``."""
+        if not self.bulk_ys:
+            return
+        cur = torch.cuda.current_stream(self.buf.device)
+        for stream in self._push_streams:
             done = torch.cuda.Event()
             done.record(stream)
             cur.wait_event(done)
 
-    def own_rows(self, B, n_points, F, dtype):
-        """This rank's rows of its own gathered buffers (ys, n_steps, n_accepted, n_initialized, status):
-        the primary outputs of the kernel launch."""
-        assert self.matches(B, n_points, F, dtype), "workspace was built for another problem shape"
-        lo, hi = self.rank * self.local_batch, (self.rank + 1) * self.local_batch
-        return (self.ys[lo:hi], self.n_steps[lo:hi], self.n_accepted[lo:hi], self.n_initialized[lo:hi],
-                self.status[lo:hi])
+    def _check(self, B, n_points, F, dtype, rows):
+        a, b = (0, self.local_batch) if rows is None else rows
+        assert (b - a == B and 0 <= a <= b <= self.local_batch
+                and (self.n_points, self.n_features, self.dtype) == (max(n_points, 1), F, dtype)), \
+            "workspace was built for another problem shape"
+        return a, b
 
-    def fill(self, sol, B, n_points, F, dtype):
+    def own_rows(self, B, n_points, F, dtype, rows=None):
+        """Rows ``[a, b)`` (default: all) of this rank's block of its own gathered buffers (ys, n_steps,
+        n_accepted, n_initialized, status): the primary outputs of the kernel launch."""
+        a, b = self._check(B, n_points, F, dtype, rows)
+        lo = self.rank * self.local_batch
+        return (self.ys[lo + a:lo + b], self.n_steps[lo + a:lo + b], self.n_accepted[lo + a:lo + b],
+                self.n_initialized[lo + a:lo + b], self.status[lo + a:lo + b])
+
+    def fill(self, sol, B, n_points, F, dtype, rows=None):
         """Set the peer_* fields of a ``tode_solution`` whose primary outputs are ``own_rows`` (called by
         ``AutoDiffAdjoint._fused_launch``): the other ranks' replicas, and everybody's global block."""
-        assert self.matches(B, n_points, F, dtype), "workspace was built for another problem shape"
+        a, _ = self._check(B, n_points, F, dtype, rows)
         G = self.world * self.local_batch
-        sol.n_peers, sol.peer_row0 = self.world, self.rank * self.local_batch
+        sol.n_peers, sol.peer_row0 = self.world, self.rank * self.local_batch + a
         for p, base in enumerate(self.bases):
             remote = p != self.rank
             sol.peer_ys[p] = base + self._off_ys if (remote and not self.bulk_ys) else None
@@ -197,11 +216,20 @@ class SymmetricWorkspace:
 
 
 def solve_sharded_symmetric(solver, local_problem: InitialValueProblem, ws: SymmetricWorkspace, *,
-                            dt0: Optional[torch.Tensor] = None, ts: Optional[torch.Tensor] = None) -> Solution:
+                            dt0: Optional[torch.Tensor] = None, ts: Optional[torch.Tensor] = None,
+                            chunks: int = 1) -> Solution:
     """Solve this rank's shard with the fused kernel writing straight into every rank's gathered
     buffers (``ws``); returns the full-batch Solution (aliasing ``ws``).  Collective: every rank
     of the group must call it.  ``ts``: the full-batch evaluation times if the caller has them
-    (else this rank's ``ts`` is gathered with NCCL)."""
+    (else this rank's ``ts`` is gathered with NCCL).
+
+    ``chunks`` (dense-output workloads): the shard is solved in that many row blocks, and the ys rows
+    of block i travel to the peers (bulk copies on their own streams) while block i + 1 solves.
+
+    A failure anywhere stops the WHOLE batch at that iteration (adjoints.py:186-190): every launch
+    publishes its iteration count and its first failing iteration to all ranks (system-scope atomics
+    of the kernel's epilogue); a shard whose samples ran past the batch-wide first failure replays
+    with that cap."""
     from .adjoints import _INT32_MAX
 
     term_ = solver.step_method.term
@@ -209,40 +237,60 @@ def solve_sharded_symmetric(solver, local_problem: InitialValueProblem, ws: Symm
     if field is None:
         raise NotImplementedError("solve_sharded_symmetric needs a built-in analytic field (the fused route); "
                                   "use solve_sharded for opaque vector fields")
+    B = local_problem.batch_size
+    n_blocks = max(1, min(int(chunks), B)) if ws.bulk_ys else 1
+    bounds = [shard_bounds(B, i, n_blocks) for i in range(n_blocks)]
+
+    def block(a, b):
+        if n_blocks == 1:
+            return local_problem, dt0
+        te = None if local_problem.t_eval is None else local_problem.t_eval[a:b]
+        return (InitialValueProblem(local_problem.y0[a:b], local_problem.t_start[a:b], local_problem.t_end[a:b], te),
+                None if dt0 is None else dt0[a:b])
+
     with torch.no_grad(), torch.cuda.device(local_problem.device):
         ws.glob.zero_()
         ws.barrier()  # every rank has reset its global block and is done with the previous results
-        ctx = solver._fused_launch(local_problem, term_, field, dt0, peers=ws)
-        ws.push_ys()
-        ws.barrier()  # every rank's kernel (and its peer stores / atomics / bulk copies) has completed
-        g_iters, g_replay, _, _ = ws.glob.tolist()  # the one host sync
-        if g_replay:
-            # some shard saw a failure before its last iteration: "any failure stops the batch"
-            # holds per shard -- that shard replays with the cap and republishes
-            iters, first_fail = ctx["summary"].tolist()[:2]
-            if first_fail != _INT32_MAX and first_fail < iters:
-                ctx["run"](first_fail)
-                ws.push_ys()
+        ctxs = []
+        for a, b in bounds:
+            prob_i, dt0_i = block(a, b)
+            ctxs.append(solver._fused_launch(prob_i, term_, field, dt0_i, peers=ws, rows=(a, b)))
+            ws.push_ys((a, b))
+        ws.wait_pushes()
+        ws.barrier()  # every rank's kernels (and their peer stores / atomics / bulk copies) have completed
+        # one host read: this rank's global block followed by the summaries of its launches
+        words = torch.cat([ws.glob[:4]] + [c["summary"][:4] for c in ctxs]).tolist()
+        (g_iters, _, g_fail_enc, _), summaries = words[:4], [words[4 + 4 * i: 8 + 4 * i] for i in range(len(ctxs))]
+        if g_fail_enc:
+            # some sample of the batch failed: the reference stops everybody at that iteration
+            g_first_fail = _INT32_MAX - g_fail_enc
+            if any(sm[0] > g_first_fail for sm in summaries):
+                for (a, b), c in zip(bounds, ctxs):
+                    c["run"](g_first_fail)
+                    ws.push_ys((a, b))
+                ws.wait_pushes()
             ws.barrier()
-            g_iters = ws.glob.tolist()[0]
-        if ctx["summary"].tolist()[2]:
+            g_iters = min(g_iters, g_first_fail)
+        if any(sm[2] for sm in summaries):
             raise NotImplementedError("non-monotone t_eval rows need the stage-wise route: use solve_sharded")
+        launches = sum(sm[3] for sm in summaries)
     G = ws.world * ws.local_batch
     stats = {"n_steps": ws.n_steps, "n_accepted": ws.n_accepted, "n_initialized": ws.n_initialized}
     if getattr(term_, "with_stats", True):
-        stats["n_f_evals"] = torch.full((1,), ctx["n_init_evals"] + ctx["n_stage_evals"] * g_iters,
+        stats["n_f_evals"] = torch.full((1,), ctxs[0]["n_init_evals"] + ctxs[0]["n_stage_evals"] * g_iters,
                                         dtype=torch.long).expand(G)
     if ts is None:
         sizes = [ws.local_batch] * ws.world
         lts = local_problem.t_eval if local_problem.t_eval is not None else local_problem.t_end[:, None]
         ts = _gather_rows(lts, sizes, ws.group)
-    solver.last_run = {"route": "fused+peer-stores", "kernel_launches": 3, "iterations": g_iters}
+    solver.last_run = {"route": "fused+peer-stores", "iterations": g_iters, "blocks": n_blocks,
+                       "kernel_launches": launches}
     return Solution(ts=ts, ys=ws.ys, stats=stats, status=ws.status)
 
 
 def solve_sharded(solver, problem: InitialValueProblem, *, dt0: Optional[torch.Tensor] = None,
                   args=None, group=None, gather: bool = True,
-                  workspace: Optional[SymmetricWorkspace] = None) -> Solution:
+                  workspace: Optional[SymmetricWorkspace] = None, chunks: int = 1) -> Solution:
     """Every rank holds (or can build) the full problem; each solves its slice.
 
     With ``gather=False`` the local Solution is returned (statistics of the slice only).  With a
@@ -253,7 +301,8 @@ def solve_sharded(solver, problem: InitialValueProblem, *, dt0: Optional[torch.T
     local_problem = shard_problem(problem, rank, world)
     dt0_local = None if dt0 is None else dt0[lo:hi]
     if workspace is not None and gather:
-        return solve_sharded_symmetric(solver, local_problem, workspace, dt0=dt0_local, ts=problem.t_eval)
+        return solve_sharded_symmetric(solver, local_problem, workspace, dt0=dt0_local, ts=problem.t_eval,
+                                       chunks=chunks)
     local = solver.solve(local_problem, dt0=dt0_local, args=args)
     if not gather:
         return local

@@ -79,6 +79,27 @@ class LotkaVolterra(BuiltinField):
         return torch.stack((dx, dz), dim=-1)
 
 
+class _KernelField(torch.autograd.Function):
+    """A field evaluated by a forward-only CUDA kernel, differentiable with respect to its input: the
+    backward pass is the vector-Jacobian product of the same computation written in PyTorch ops
+    (``forward_reference``), recomputed from the saved input."""
+
+    @staticmethod
+    def forward(ctx, field, t, y):
+        ctx.field, ctx.t = field, t
+        ctx.save_for_backward(y)
+        return field._forward_kernel(t, y)
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        with torch.enable_grad():
+            yr = y.detach().requires_grad_()
+            out = ctx.field.forward_reference(ctx.t, yr)
+            (gy,) = torch.autograd.grad(out, yr, g)
+        return None, None, gy
+
+
 class TanhMLP256(nn.Module):
     """Neural-ODE vector field ``y -> W_L tanh(... tanh(W_1 y + b_1) ...) + b_L`` of width 256
     (BASELINE.json configs[3]) evaluated by ONE hand-written tcgen05 kernel per call: bf16 tensor
@@ -111,8 +132,12 @@ class TanhMLP256(nn.Module):
         return self.weights.shape[0]
 
     def forward(self, t, y):
-        import ctypes as C
+        # weights are buffers (inference field): gradients flow to the state only
+        if torch.is_grad_enabled() and y.requires_grad:
+            return _KernelField.apply(self, t, y)
+        return self._forward_kernel(t, y)
 
+    def _forward_kernel(self, t, y):
         from . import _launch
 
         _launch.require_cuda(y, self.weights)
@@ -146,6 +171,11 @@ class Heat1D(nn.Module):
         self.kappa = float(kappa)
 
     def forward(self, t, y):
+        if torch.is_grad_enabled() and y.requires_grad:
+            return _KernelField.apply(self, t, y)
+        return self._forward_kernel(t, y)
+
+    def _forward_kernel(self, t, y):
         from . import _launch
 
         _launch.require_cuda(y)

@@ -148,6 +148,7 @@ class _AdaptiveController(StepSizeController[_AdaptiveState]):
         c.dt_max = 0.0 if self.dt_max is None else float(self.dt_max)
         c.almost_zero = _almost_zero(data_dtype)
         c.max_steps = -1 if max_steps is None else int(max_steps)
+        c.iter_cap = 0
         return c
 
     # ---- plug-in protocol ---------------------------------------------------------
