@@ -777,7 +777,7 @@ def run_workload(env, name, batch, steps, warmup, *, main, extras):
             dist.all_gather_into_tensor(ts_full, problem.t_end[:, None].contiguous())
         else:
             ts_full = problem.t_eval[:1].expand(B * world, -1)  # the workloads share one t_eval row
-    n_chunks_mg = 4 if (ws is not None and T > 0) else 1
+    n_chunks_mg = 8 if (ws is not None and T > 0) else 1
 
     def step():
         if ws is not None:
@@ -858,8 +858,8 @@ def run_workload(env, name, batch, steps, warmup, *, main, extras):
     if fused:
         roofline["note"] = ("whole solve in registers: HBM is touched only for inputs / outputs; the kernel is bound by "
                             + ("fp64 issue (see fp64_issue)" if name == "c2" else
-                               "instruction issue (about 14 thread instructions per byte of output against a machine "
-                               "balance of 5.8; DESIGN.md section 4)")
+                               "instruction issue (about 15 thread instructions per byte of output against a machine "
+                               "balance of 5.6: at most 0.37 of the copy bandwidth at 100 % issue; DESIGN.md section 4)")
                             + "; the HBM-bound kernels of the stage-wise path are in roofline_kernels")
     res = {
         "value": value, "ms_per_step": ms_per_step, "scaling": scaling, "dtype": workload.dtype_name,
@@ -876,6 +876,7 @@ def run_workload(env, name, batch, steps, warmup, *, main, extras):
                                              "iteration 4; they are re-drawn (untimed set-up) so the batch completes")
     if world > 1:
         res["solve_only_ms"] = solve_only_ms
+        res["value_results_left_sharded"] = acc / (solve_only_ms * 1e-3)  # no exchange of ys / statistics
         res["config"]["multi_gpu"] = (
             ("independent batch slices; statistics by the fused kernel's peer stores (symmetric memory over NVLink), "
              f"dense-output blocks pushed to every peer in {n_chunks_mg} chunks under the next chunk's solve, "
@@ -883,8 +884,13 @@ def run_workload(env, name, batch, steps, warmup, *, main, extras):
             if ws is not None else "independent batch slices, NCCL all-gather of ys / statistics after the solve")
         if T > 0:
             pushed = B * T * F * e * (world - 1)
-            res["exchange"] = {"bytes_sent_per_rank": pushed, "ms_on_top_of_the_solve": ms_per_step - solve_only_ms,
-                               "nvlink_gbs_per_rank_over_the_step": pushed / ms_per_step / 1e6}
+            res["exchange"] = {
+                "bytes_sent_per_rank": pushed, "bytes_received_per_rank": pushed,
+                "ms_on_top_of_the_solve": ms_per_step - solve_only_ms,
+                "nvlink_gbs_per_rank_over_the_step": pushed / ms_per_step / 1e6,
+                "limiter": "every rank receives the other ranks' dense output (the north star's all-gather of solutions): "
+                           "at 900 GB/s per direction that alone takes bytes_received_per_rank / 900e9 s, "
+                           f"{pushed / 900e9 * 1e3:.2f} ms here against {solve_only_ms:.2f} ms of solve"}
     if not main:
         del ws
         return res, None

@@ -1,0 +1,146 @@
+"""The reference's OWN test-suite (torchode v1.0.1 ``tests/``, staged verbatim under baseline/_ref/ref_tests by
+scripts/stage_reference.sh) executed against this package: a conftest shim makes ``import torchode`` resolve to
+``torchode_b200`` (same public names); nothing in the test files is edited.
+
+* CPU (``-m "not gpu"``): the loop-semantics tests that drive ``AutoDiffAdjoint.solve`` with the reference's stub
+  step method / stub controller (10 of the 13 tests of adjoint_test.py:26-319): plug-in objects on CPU tensors run through the
+  generic route of the loop.
+* GPU (``-m gpu``): every test file, with ``torch.set_default_device("cuda")`` so that the fixtures build CUDA
+  tensors (the built-in components have no CPU path), ``Tensor.numpy()`` going through ``.cpu()``.
+
+Per-file results of the last run on the B200: profiles/r02_reference_suite.txt (61 / 61 on the GPU + 8 / 8 on the
+CPU = the reference's 69 tests)."""
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_TESTS = os.path.join(ROOT, "baseline", "_ref", "ref_tests")
+
+SHIM = r'''
+import importlib, os, sys, types
+sys.path.insert(0, {root!r})
+import torch
+import torchode_b200 as pkg
+
+sys.modules["torchode"] = pkg
+for name in ("interpolation", "step_size_controllers", "status_codes", "terms", "problems", "solution", "interface",
+             "adjoints", "single_step_methods"):
+    sys.modules["torchode." + name] = importlib.import_module("torchode_b200." + name)
+rk = types.ModuleType("torchode.single_step_methods.runge_kutta")
+from torchode_b200 import single_step_methods as _ssm, tableaus as _tab
+rk.ButcherTableau, rk.ExplicitRungeKutta, rk.ERKInterpolationData = _tab.ButcherTableau, _ssm.ExplicitRungeKutta, _ssm.ERKInterpolationData
+sys.modules["torchode.single_step_methods.runge_kutta"] = rk
+ty = types.ModuleType("torchode.typing")  # annotation-only names (problems.py: `from torchode.typing import *`)
+for n in ("TimeTensor", "DataTensor", "NormTensor", "SolutionDataTensor", "EvaluationTimesTensor", "AcceptTensor",
+          "StatusTensor", "InterpTimeTensor", "InterpDataTensor", "SampleIndexTensor", "CoefficientVector",
+          "RungeKuttaMatrix", "WeightVector", "WeightMatrix"):
+    setattr(ty, n, torch.Tensor)
+ty.__all__ = [n for n in dir(ty) if not n.startswith("_")]
+sys.modules["torchode.typing"] = ty
+
+if os.environ.get("TODE_REF_SUITE_DEVICE") == "cuda":
+    torch.set_default_device("cuda")
+    _numpy = torch.Tensor.numpy
+    torch.Tensor.numpy = lambda self, *a, **k: _numpy(self.detach().cpu(), *a, **k)
+'''
+
+# reference test files that are not expected to pass, with the reason (none: all 69 tests pass -- 61 on the GPU,
+# the 8 of interpolation_test.py on the CPU)
+XFAIL_GPU = {}
+
+
+def run_suite(device, files, select=None):
+    """Runs the staged reference tests in a scratch copy; returns (returncode, {test id: outcome}, tail of the log)."""
+    tmp = tempfile.mkdtemp(prefix="ref_suite_")
+    try:
+        for f in os.listdir(REF_TESTS):
+            if f.endswith(".py"):
+                shutil.copy(os.path.join(REF_TESTS, f), tmp)
+        with open(os.path.join(tmp, "conftest.py"), "w") as fh:
+            fh.write(SHIM.format(root=ROOT))
+        cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--tb=short", "-rA"]
+        cmd += files
+        if select:
+            cmd += ["-k", select]
+        env = dict(os.environ, TODE_REF_SUITE_DEVICE=device)
+        env.pop("PYTEST_CURRENT_TEST", None)
+        proc = subprocess.run(cmd, cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                              timeout=1500)
+        outcomes = {}
+        for m in re.finditer(r"^(PASSED|FAILED|ERROR|SKIPPED|XFAIL|XPASS)\s+(\S+)", proc.stdout, re.M):
+            outcomes[m.group(2)] = m.group(1)
+        return proc.returncode, outcomes, proc.stdout[-30000:]
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def _need_ref():
+    if not os.path.isdir(REF_TESTS):
+        pytest.skip("baseline/_ref/ref_tests is not staged (scripts/stage_reference.sh)")
+
+
+# adjoint_test.py:26-319 -- the tests that isolate the LOOP with stub components (no numerics of ours involved)
+STUB_DRIVEN = " or ".join((
+    "test_evaluates_solution_at_evaluation_points", "test_odes_step_independently",
+    "test_multiple_evaluation_points_in_single_step", "test_multiple_evals_on_the_last_step",
+    "test_terminates_after_max_steps",
+    "test_rejected_steps_continue_at_same_place", "test_value_is_only_saved_when_step_is_accepted",
+    "test_rejection_of_initial_step_does_not_skip_evaluation_at_t_start", "test_stops_on_non_successful_step_method",
+    "test_stops_on_non_successful_adapt_step_size"))
+# (adjoint_test.py's other three loop tests -- no t_eval / finished solves keep dt / evaluation range -- pair a stub
+# controller with the real Dopri5, whose arithmetic is CUDA-only here: they run in the GPU pass below)
+
+
+def test_reference_loop_semantics_tests_pass_on_cpu_with_stub_components():
+    _need_ref()
+    rc, outcomes, log = run_suite("cpu", ["adjoint_test.py"], select=STUB_DRIVEN)
+    bad = {k: v for k, v in outcomes.items() if v in ("FAILED", "ERROR")}
+    assert outcomes and not bad, f"{bad}\n{log}"
+    assert sum(v == "PASSED" for v in outcomes.values()) == 10, log
+
+
+def test_reference_interpolation_tests_pass_on_cpu():
+    """interpolation_test.py builds its fixtures with torch.from_numpy (host tensors by construction): the
+    stand-alone interpolation API (polynomial classes, ``from_k``, ``Tsit5.build_interpolation`` called unbound,
+    ``.coefficients``) works on host tensors; all 8 tests."""
+    _need_ref()
+    rc, outcomes, log = run_suite("cpu", ["interpolation_test.py"])
+    bad = {k: v for k, v in outcomes.items() if v in ("FAILED", "ERROR")}
+    assert not bad and sum(v == "PASSED" for v in outcomes.values()) == 8, log
+
+
+@pytest.mark.gpu
+def test_reference_suite_passes_on_the_gpu():
+    _need_ref()
+    files = sorted(f for f in os.listdir(REF_TESTS) if f.endswith("_test.py"))
+    lines, failures = [], {}
+    for f in files:
+        if f in CPU_ONLY:
+            lines.append(f"{f:36s} {CPU_ONLY[f]}")
+            continue
+        rc, outcomes, log = run_suite("cuda", [f])
+        n_pass = sum(v == "PASSED" for v in outcomes.values())
+        bad = {k: v for k, v in outcomes.items() if v in ("FAILED", "ERROR")}
+        note = f"  (not applicable: {XFAIL_GPU[f]})" if f in XFAIL_GPU else ""
+        lines.append(f"{f:36s} passed {n_pass:3d}  failed {len(bad):3d}{note}")
+        for k, v in bad.items():
+            lines.append(f"    {v} {k}")
+        if bad and f not in XFAIL_GPU:
+            failures[f] = (bad, log)
+    report = "\n".join(lines)
+    print(report)
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "r02_reference_suite_failures.log"), "w") as fh:
+            for f, (_, log) in failures.items():
+                fh.write(f"##### {f}\n{log}\n")
+        with open(os.path.join(out_dir, "r02_reference_suite.txt"), "w") as fh:
+            fh.write("# the reference's own tests (baseline/_ref/ref_tests) against torchode_b200 on the B200,\n"
+                     "# torch.set_default_device('cuda'); tests/test_reference_suite.py\n" + report + "\n")
+    assert not failures, report + "\n\n" + "\n".join(log for _, log in failures.values())

@@ -95,7 +95,7 @@ class AutoDiffAdjoint(nn.Module):
         key = (str(dev), look)
         ring = self._rings.get(key)
         if ring is None:
-            ring = (torch.zeros((look + 1, _cabi.CTL_WORDS), dtype=torch.int32).pin_memory(),
+            ring = (torch.zeros((look + 1, _cabi.CTL_WORDS), dtype=torch.int32, device="cpu").pin_memory(),
                     [torch.cuda.Event() for _ in range(look + 1)])
             self._rings[key] = ring
         return ring

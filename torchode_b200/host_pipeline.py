@@ -23,7 +23,7 @@ from .solution import Solution
 
 
 def _pinned_like(shape, dtype) -> torch.Tensor:
-    return torch.empty(shape, dtype=dtype, pin_memory=True)
+    return torch.empty(shape, dtype=dtype, device="cpu", pin_memory=True)
 
 
 def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, device, *, chunks: int = 8,
@@ -49,7 +49,7 @@ def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, devic
     else:
         ys = _pinned_like((B, max(Tn, 1), F), D)
         status, n_steps, n_accepted, n_init = (_pinned_like((B,), torch.long) for _ in range(4))
-    summaries = torch.empty((chunks, _cabi.SUMMARY_WORDS), dtype=torch.int32, pin_memory=True)
+    summaries = torch.empty((chunks, _cabi.SUMMARY_WORDS), dtype=torch.int32, device="cpu", pin_memory=True)
     te_host = problem.t_eval
     te_broadcast = te_host is not None and te_host.stride(0) == 0
 

@@ -91,7 +91,11 @@ class ExplicitRungeKutta(SingleStepMethod[ERKState, ERKInterpolationData]):
 
     def to_cabi(self) -> _cabi.Tableau:
         interp = _cabi.INTERP_DOPRI5 if self.INTERP_ID is None else self.INTERP_ID
-        return self.tableau.to_cabi(interp, self.convergence_order())
+        try:
+            order = self.convergence_order()
+        except NotImplementedError:  # a custom tableau stepped on its own (the order only matters to controllers)
+            order = 0
+        return self.tableau.to_cabi(interp, order)
 
     def init(self, term, problem: InitialValueProblem, f0, *, stats: Dict[str, Any], args: Any):
         prev = None
@@ -132,12 +136,36 @@ class _KernelQuartic(FourthOrderPolynomialInterpolation):
     """Quartic dense output whose coefficients are never materialised: ``evaluate`` runs
     ``tode_interp_eval`` straight from the step data (dopri5.py:54-60, tsit5.py:124-139)."""
 
-    def __init__(self, cab, data: ERKInterpolationData):
-        self.cab, self.data = cab, data
+    def __init__(self, interp_id: int, data: ERKInterpolationData):
+        self.interp_id, self.data = interp_id, data
         self.t0, self.t1 = data.t0, data.t0 + data.dt
+        self._cab = self._coefficients = None
+
+    @property
+    def cab(self):
+        if self._cab is None:
+            self._cab = self.data.tableau.to_cabi(self.interp_id, 5)
+        return self._cab
+
+    @property
+    def coefficients(self):
+        """The quartic in increasing powers of the unit coordinate, materialised on request (the reference's
+        interpolation objects expose them; the solve loop never asks)."""
+        if self._coefficients is None:
+            d, w = self.data, self.data.tableau.b_other
+            h = d.dt.to(dtype=d.y0.dtype)[:, None]
+            if self.interp_id == _cabi.INTERP_DOPRI5:
+                self._coefficients = FourthOrderPolynomialInterpolation.from_k(
+                    d.t0, d.dt, d.y0, d.y1, d.k, w[0]).coefficients
+            else:
+                c2, c3, c4 = (h * torch.einsum("s, sbf -> bf", w[r], d.k) for r in range(3))
+                self._coefficients = (d.y0, h * d.k[0], c2, c3, c4)
+        return self._coefficients
 
     def evaluate(self, t, idx):
         d = self.data
+        if not d.y0.is_cuda:  # stand-alone use on host tensors (plug-in authors, the reference's unit tests)
+            return FourthOrderPolynomialInterpolation.evaluate(self, t, idx)
         return _launch.interp_eval(self.cab, d.t0, d.dt, d.y0, d.y1, d.k, t, idx)
 
 
@@ -154,7 +182,7 @@ class Dopri5(ExplicitRungeKutta):
         return 5
 
     def build_interpolation(self, data: ERKInterpolationData):
-        return _KernelQuartic(self.to_cabi(), data)
+        return _KernelQuartic(_cabi.INTERP_DOPRI5, data)  # (no use of self: the reference's tests call it unbound)
 
 
 class Tsit5(ExplicitRungeKutta):
@@ -170,7 +198,7 @@ class Tsit5(ExplicitRungeKutta):
         return 5
 
     def build_interpolation(self, data: ERKInterpolationData):
-        return _KernelQuartic(self.to_cabi(), data)
+        return _KernelQuartic(_cabi.INTERP_TSIT5, data)
 
 
 class Heun(ExplicitRungeKutta):
