@@ -40,12 +40,16 @@ def test_kernel_matches_fp32_reference(B, n_layers):
         got = field(None, y)
         want = field.forward_reference(None, y)
     torch.cuda.synchronize()
-    # fp32 accumulation order differs (tensor core vs cuBLAS/fp32 matmul); bf16 re-rounding of the
-    # hidden activations can flip a last bf16 bit: tolerance 2e-2 of the output scale, typical 1e-5
+    # same bf16 operands, fp32 accumulation on both sides: what differs is the accumulation order (tensor core vs
+    # fp32 matmul), tanh.approx (2^-11 relative) and, through them, a last bf16 bit of a hidden activation
+    # (2^-8 relative of that activation, times a weight of the next layer).  Measured worst case over these
+    # shapes: 1e-3 of the output scale (round 1 asserted 2e-2); bound 4e-3, median 1e-4.
     scale = want.abs().max()
     assert torch.isfinite(got).all()
-    assert (got - want).abs().max() <= 2e-2 * scale
-    assert (got - want).abs().median() <= 1e-4 * scale
+    err = (got - want).abs()
+    print(f"B={B} layers={n_layers}: max err {float(err.max() / scale):.2e} of the output scale, median {float(err.median() / scale):.2e}")
+    assert err.max() <= 4e-3 * scale
+    assert err.median() <= 1e-4 * scale
 
 
 def test_solve_around_the_mlp_field_matches_the_oracle_loop():

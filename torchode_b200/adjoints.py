@@ -65,11 +65,13 @@ class AutoDiffAdjoint(nn.Module):
         #: how many loop iterations the host may run ahead of the device (staged route)
         self.lookahead = 3
         #: staged route: capture one loop iteration (6 x (stage kernel, f) + finish kernel) into a
-        #: CUDA graph after the first, eagerly launched iteration and replay it.  Opt-in, because
-        #: the Python body of ``f`` then runs only once more (at capture): ``f`` must be
-        #: capturable (no host sync, no data-dependent Python control flow) and free of host side
-        #: effects.  Removes the launch latency that dominates small problems.
-        self.use_cuda_graph = False
+        #: CUDA graph after the first, eagerly launched iteration and replay it.  Removes the launch
+        #: latency that dominates small problems.  ``None`` (default) = automatic: on when ``f`` is one of
+        #: this package's kernel fields (``fields.TanhMLP256``: known to be capturable and free of host
+        #: side effects), off for user code, because the Python body of ``f`` then runs only once
+        #: more (at capture): an opaque ``f`` must be capturable (no host sync, no data-dependent Python
+        #: control flow) and must not count its calls or log on the host -- set ``True`` to opt in.
+        self.use_cuda_graph: Optional[bool] = None
         #: stage-wise route with the built-in ``fields.Heat1D`` as f and no ``t_eval``: run a whole loop
         #: iteration as ONE pass over y (stage values and the stencil's neighbours stay on chip,
         #: ``tode_heat_step``) instead of 6 x (stage kernel, f) + finish.  With ``fields.TanhMLP256`` as
@@ -295,7 +297,10 @@ class AutoDiffAdjoint(nn.Module):
         cab_c.iter_cap = int(iter_cap)
         S = cab_t.n_stages
         plan = None
-        if self.use_cuda_graph and record is None:
+        use_graph = self.use_cuda_graph
+        if use_graph is None:  # automatic: only for fields known to be pure and capturable
+            use_graph = type(term_.f) is TanhMLP256 and plain_term_of(term_) and args is None
+        if use_graph and record is None:
             te = problem.t_eval
             key = (str(dev), B, F, Tn, D, Tt, general, step_fusion, stage_fusion, id(term_.f), id(args), dt0 is None,
                    None if te is None else (te.stride(0) == 0), bytes(cab_t), bytes(cab_c))
