@@ -129,7 +129,9 @@ def test_c4_same_kernel_field_in_the_reference_loop_on_the_same_gpu(ref):
     """configs[3] has no CPU fixture: bf16 GEMMs differ between CPU and GPU far above the solver tolerance
     (SURVEY.md 8(d)), so parity is checked with the SAME f -- this repo's tcgen05 field module as the ``f`` of the
     reference's ODETerm -- in the reference's eager loop on the same GPU.  What differs is then only the solver
-    arithmetic (this repo's kernels vs the reference's eager ops)."""
+    arithmetic.  The field rounds its input to bf16, so a one-ulp (fp32) change of a stage value can move f by
+    2^-8 relative: at rtol 1e-3 the accept decisions are chaotic.  The bound is therefore the reference's own
+    sensitivity, measured in the same test: its loop around f(t, y) against its loop around f(t, y (1 + 2^-23))."""
     bench = _bench()
     to_ref = ref.load()
     B = 2048
@@ -141,19 +143,38 @@ def test_c4_same_kernel_field_in_the_reference_loop_on_the_same_gpu(ref):
     with torch.no_grad():
         ours = solver.solve(bench.make_problem(host, DEV))
     assert solver.last_run["route"] == "stage-fused+graph"
-    rterm = to_ref.ODETerm(field)
-    rsolver = to_ref.AutoDiffAdjoint(to_ref.Dopri5(term=rterm), to_ref.IntegralController(1e-6, 1e-3, term=rterm)).to(DEV)
-    with torch.no_grad():
-        theirs = rsolver.solve(to_ref.InitialValueProblem(y0=host["y0"].to(DEV), t_start=host["t_start"].to(DEV),
-                                                          t_end=host["t_end"].to(DEV)))
-    torch.cuda.synchronize()
-    (sa, aa, ta), (sb, ab, tb) = _counts(ours), _counts(theirs)
-    same = (sa == sb) & (aa == ab)
-    ya, yb = ours.ys.cpu().numpy(), theirs.ys.cpu().numpy()
-    rel = (np.abs(ya - yb) / np.abs(yb).max(axis=-1, keepdims=True)).reshape(B, -1).max(axis=1)
-    print(f"C4 B={B}: count-mismatch fraction {1 - same.mean():.4f}; iterations ours "
-          f"{int(ours.stats['n_f_evals'][0])} reference {int(theirs.stats['n_f_evals'][0])}; "
-          f"ys err / row norm: median {np.median(rel):.2e}, max over same-count rows {rel[same].max():.2e}")
-    assert np.array_equal(ta, tb)
-    assert 1 - same.mean() <= 0.02
-    assert np.median(rel[same]) <= 1e-5
+
+    def reference_run(f, y0):
+        rterm = to_ref.ODETerm(f)
+        rsolver = to_ref.AutoDiffAdjoint(to_ref.Dopri5(term=rterm), to_ref.IntegralController(1e-6, 1e-3, term=rterm)).to(DEV)
+        with torch.no_grad():
+            sol = rsolver.solve(to_ref.InitialValueProblem(y0=y0, t_start=host["t_start"].to(DEV),
+                                                           t_end=host["t_end"].to(DEV)))
+        torch.cuda.synchronize()
+        return sol
+
+    y0 = host["y0"].to(DEV)
+    theirs = reference_run(field, y0)
+    # the reference against itself under one-ulp noise: (a) on the initial condition (every later value then
+    # differs by rounding-level amounts, like between two implementations), (b) on every input of f
+    nudged_y0 = reference_run(field, y0 * (1 + 2.0 ** -23))
+    nudged_f = reference_run(lambda t, y: field(t, y * (1 + 2.0 ** -23)), y0)
+
+    def compare(a, b):
+        (sa, aa, ta), (sb, ab, tb) = _counts(a), _counts(b)
+        assert np.array_equal(ta, tb)
+        ya, yb = a.ys.cpu().numpy(), b.ys.cpu().numpy()
+        rel = (np.abs(ya - yb) / np.abs(yb).max(axis=-1, keepdims=True)).reshape(B, -1).max(axis=1)
+        return float(1 - ((sa == sb) & (aa == ab)).mean()), float(np.median(rel)), float(np.quantile(rel, 0.9))
+
+    m_ours, y_ours, y90_ours = compare(ours, theirs)
+    m_y0, y_y0, y90_y0 = compare(nudged_y0, theirs)
+    m_f, y_f, y90_f = compare(nudged_f, theirs)
+    print(f"C4 B={B}: count-mismatch fraction / median / p90 of ys err per row norm -- ours vs reference {m_ours:.4f} / "
+          f"{y_ours:.2e} / {y90_ours:.2e}; reference vs reference with y0 (1 + 2^-23) {m_y0:.4f} / {y_y0:.2e} / {y90_y0:.2e}; "
+          f"reference vs reference with f(y (1 + 2^-23)) {m_f:.4f} / {y_f:.2e} / {y90_f:.2e}; loop iterations "
+          f"{int(ours.stats['n_f_evals'][0])} / {int(theirs.stats['n_f_evals'][0])}")
+    floor_m, floor_y = max(m_y0, m_f), max(y90_y0, y90_f)
+    assert m_ours <= floor_m * 1.15 + 0.02
+    assert y90_ours <= floor_y * 2 + 1e-5
+    assert abs(ours.stats["n_steps"].float().mean().item() / theirs.stats["n_steps"].float().mean().item() - 1) < 0.02

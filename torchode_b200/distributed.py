@@ -142,6 +142,12 @@ class SymmetricWorkspace:
         # with t_eval the kernel replicates only the statistics and this rank's finished ys block is
         # pushed to the peers in bulk (one device-to-device copy per peer, each on its own stream).
         self.bulk_ys = self.n_points > 1
+        # ... over copy-engine pushes between TWO GPUs (750 GB/s; NCCL's all-gather: 515 GB/s).  With more
+        # ranks every GPU has N - 1 pushes in flight in each direction and the copy engines get 300-340 GB/s per
+        # rank (measured at N = 4 and 8), where NCCL's in-place all-gather of the same blocks reaches 590 GB/s:
+        # from three ranks on the dense-output block goes through NCCL (profiles/r02_symmetric_8gpu.txt)
+        self.push_by_copy = self.bulk_ys and self.world == 2
+        self._ys_flat = self.buf[self._off_ys: self._off_ys + G * self.n_points * n_features * esz].view(dtype)
         if self.bulk_ys:
             lo = self.rank * local_batch
             self._ys_local = self.ys[lo: lo + local_batch]
@@ -164,7 +170,7 @@ class SymmetricWorkspace:
         buffer, one device-to-device copy per peer on that peer's push stream, ordered after what is on
         the current stream now.  The current stream does NOT wait: the next chunk's solve overlaps the
         copies; ``wait_pushes`` joins them."""
-        if not self.bulk_ys:
+        if not self.bulk_ys or not self.push_by_copy:
             return
         a, b = (0, self.local_batch) if rows is None else rows
         cur = torch.cuda.current_stream(self.buf.device)
@@ -177,8 +183,15 @@ class SymmetricWorkspace:
                 dst[a:b].copy_(self._ys_local[a:b], non_blocking=True)
 
     def wait_pushes(self):
-        """The current stream waits for every bulk copy enqueued by ``push_ys``."""
+        """The current stream waits for every bulk copy enqueued by ``push_ys`` -- or, with more than two
+        ranks, runs the in-place NCCL all-gather of the ranks' dense-output blocks (this rank's block already
+        sits at its place in the gathered buffer: no staging copy)."""
         if not self.bulk_ys:
+            return
+        if not self.push_by_copy:
+            block = self.local_batch * self.n_points * self.n_features
+            dist.all_gather_into_tensor(self._ys_flat, self._ys_flat[self.rank * block:(self.rank + 1) * block],
+                                        group=self.group)
             return
         cur = torch.cuda.current_stream(self.buf.device)
         for stream in self._push_streams:
@@ -238,7 +251,7 @@ def solve_sharded_symmetric(solver, local_problem: InitialValueProblem, ws: Symm
         raise NotImplementedError("solve_sharded_symmetric needs a built-in analytic field (the fused route); "
                                   "use solve_sharded for opaque vector fields")
     B = local_problem.batch_size
-    n_blocks = max(1, min(int(chunks), B)) if ws.bulk_ys else 1
+    n_blocks = max(1, min(int(chunks), B)) if (ws.bulk_ys and ws.push_by_copy) else 1
     bounds = [shard_bounds(B, i, n_blocks) for i in range(n_blocks)]
 
     def block(a, b):
@@ -264,10 +277,14 @@ def solve_sharded_symmetric(solver, local_problem: InitialValueProblem, ws: Symm
         if g_fail_enc:
             # some sample of the batch failed: the reference stops everybody at that iteration
             g_first_fail = _INT32_MAX - g_fail_enc
-            if any(sm[0] > g_first_fail for sm in summaries):
+            replay = any(sm[0] > g_first_fail for sm in summaries)
+            if replay:
                 for (a, b), c in zip(bounds, ctxs):
                     c["run"](g_first_fail)
                     ws.push_ys((a, b))
+            if replay or not ws.push_by_copy:
+                # (the NCCL gather of the dense-output blocks is a collective: every rank takes part, whether
+                # its own shard replayed or not -- all ranks read the same global block, so all are here)
                 ws.wait_pushes()
             ws.barrier()
             g_iters = min(g_iters, g_first_fail)
