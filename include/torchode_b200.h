@@ -311,6 +311,16 @@ int tode_mlp_tanh256_stage_forward(const tode_tableau* tab, int stage, const tod
                                    const void* const* k, void* y_out, const void* weights_bf16,
                                    const void* biases_f32, void* out, int32_t n_layers, void* stream);
 
+/* Step-fused evaluation (ABI 3): ALL stages of one explicit RK step around the MLP field in ONE launch --
+ * for i = 1 .. n_stages-1:  y_i = y + dt * sum_{j<i} a[i][j] k[j],  k[i] = f(y_i)   (runge_kutta.py:259-263;
+ * f autonomous).  k[0] = f(t, y) on entry (FSAL slot), k[1 .. n_stages-1] are outputs ((B,256) fp32 each);
+ * y1_out (may be NULL) receives y_{n_stages-1} (the step's y1 for an SSAL tableau).  f acts row by row, so
+ * a CTA runs the stages of its rows back to back with no grid-wide synchronisation.  Same bits as
+ * n_stages-1 calls of tode_mlp_tanh256_stage_forward. */
+int tode_mlp_tanh256_step_forward(const tode_tableau* tab, const tode_state* st, void* const* k,
+                                  void* y1_out, const void* weights_bf16, const void* biases_f32,
+                                  int32_t n_layers, void* stream);
+
 /* Method-of-lines vector field of the 1-D heat equation with Dirichlet ends (configs[4]), one
  * HBM pass: out[b,i] = kappa * ((y[b,i+1] - 2 y[b,i]) + y[b,i-1]) for 0 < i < N-1, 0 at the ends;
  * y, out (B,N) row-major, 16-byte aligned, N divisible by 4 (f32) / 2 (f64).  A user-level f like

@@ -120,6 +120,31 @@ def test_stage_fused_evaluation_equals_stage_kernel_then_field(B, tdtype, method
     assert (got == 7.0).all()
 
 
+@pytest.mark.parametrize("B", [700, 8192, 19000])  # 19000: 128-row tiles
+@pytest.mark.parametrize("method", [to.Dopri5, to.Tsit5])
+def test_all_stages_in_one_launch_equal_one_launch_per_stage(B, method):
+    """tode_mlp_tanh256_step_forward (round 2: a CTA walks the six stages of its rows) against six
+    tode_mlp_tanh256_stage_forward launches: same bits in every k_i, y1 and the whole solve."""
+    field = make_field(3)
+    g = torch.Generator().manual_seed(B)
+    problem = to.InitialValueProblem(torch.randn(B, 256, generator=g).to(DEV), torch.zeros(B, device=DEV),
+                                     (0.3 + 0.4 * torch.rand(B, generator=g)).to(DEV))
+    term = to.ODETerm(field)
+    sols = {}
+    for mode in (True, "stages"):
+        solver = to.AutoDiffAdjoint(method(term), to.IntegralController(1e-6, 1e-3, term=term))
+        solver.use_step_fusion = mode
+        solver.use_cuda_graph = False
+        with torch.no_grad():
+            sols[mode] = solver.solve(problem)
+        assert solver.last_run["route"] == "stage-fused"
+    a, b = sols[True], sols["stages"]
+    assert bits_equal(a.ys.cpu().numpy(), b.ys.cpu().numpy())
+    for key in ("n_steps", "n_accepted", "n_f_evals"):
+        assert a.stats[key].cpu().tolist() == b.stats[key].cpu().tolist()
+    assert (a.status == 0).all()
+
+
 @pytest.mark.parametrize("graph", [False, True])
 def test_stage_fused_route_is_bit_identical_to_the_stage_wise_route(graph):
     field = make_field(3)

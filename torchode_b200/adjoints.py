@@ -391,14 +391,23 @@ class AutoDiffAdjoint(nn.Module):
             # for the last stage (the finish kernel's y1)
             mlp = term_.f
             for i in range(1, S):
-                k_i = torch.empty_like(st.y)
-                y_out = y_stage[S - 2].data_ptr() if i == S - 1 else None
-                rc = lib.tode_mlp_tanh256_stage_forward(tab_p, i, st_p, kp, y_out, mlp.weights.data_ptr(),
-                                                        mlp.biases.data_ptr(), k_i.data_ptr(), mlp.n_layers, stream)
+                ks[i] = torch.empty_like(st.y)  # kept alive until the finish kernel has consumed it
+                kp[i] = ks[i].data_ptr()
+            if self.use_step_fusion == "stages":  # one launch per stage (round 1)
+                for i in range(1, S):
+                    y_out = y_stage[S - 2].data_ptr() if i == S - 1 else None
+                    rc = lib.tode_mlp_tanh256_stage_forward(tab_p, i, st_p, kp, y_out, mlp.weights.data_ptr(),
+                                                            mlp.biases.data_ptr(), kp[i], mlp.n_layers, stream)
+                    if rc:
+                        _cabi.check(rc, "tode_mlp_tanh256_stage_forward")
+            else:
+                # all six stage evaluations in ONE launch: rows are independent, so a CTA walks the stages of
+                # its rows without any grid-wide synchronisation (tode_mlp_tanh256_step_forward)
+                rc = lib.tode_mlp_tanh256_step_forward(tab_p, st_p, kp, y_stage[S - 2].data_ptr(),
+                                                       mlp.weights.data_ptr(), mlp.biases.data_ptr(), mlp.n_layers,
+                                                       stream)
                 if rc:
-                    _cabi.check(rc, "tode_mlp_tanh256_stage_forward")
-                ks[i] = k_i  # keep alive until the finish kernel has consumed it
-                kp[i] = k_i.data_ptr()
+                    _cabi.check(rc, "tode_mlp_tanh256_step_forward")
             rc = finish(tab_p, ctrl_p, st_p, kp, y_stage[S - 2].data_ptr(), stream)
             if rc:
                 _cabi.check(rc, "tode_erk_finish")
@@ -472,8 +481,9 @@ class AutoDiffAdjoint(nn.Module):
                          "general": general,
                          "iterations_launched": launched,
                          # 6 stage kernels + finish (3 launches in split mode) per launched iteration
-                         # (step-fused: 2 launches), + init
-                         "kernel_launches_min": launched * (2 if step_fusion else S) + (2 if dt0 is None else 1)}
+                         # (step-fused heat route and MLP field with all stages in one launch: 2), + init
+                         "kernel_launches_min": launched * (2 if (step_fusion or (
+                             stage_fusion and self.use_step_fusion != "stages")) else S) + (2 if dt0 is None else 1)}
         # speculative iterations after the stop flag are no-ops on the device
         if plain_term:
             _uniform_stats(term_, problem, stats, n_init_evals + (S - 1) * iters)

@@ -206,14 +206,19 @@ __device__ __forceinline__ void epilogue_m64(uint32_t tmem_base, uint8_t* sA, ui
 // with the arithmetic of erk_stage_kernel (product, FMA chain in ascending j, one FMA with dt), so
 // that the launch replaces tode_erk_stage + tode_mlp_tanh256_forward bit for bit.  nk == 0: plain
 // evaluation of y.
+//
+// Step-fused evaluation (tode_mlp_tanh256_step_forward, round 2): stages stage0 .. stage1 in ONE launch.  f acts
+// row by row, so a CTA's rows never need another CTA's results: the CTA forms y_i from the k_j it wrote itself a
+// stage earlier (global memory, L2-resident), evaluates the MLP, writes k_i and goes on -- no grid-wide
+// synchronisation, one launch + ramp-up instead of six, TMEM and barriers set up once.
 constexpr int kMaxStageK = 6;
 struct StageIn {
-  const float* k[kMaxStageK];
-  float a[kMaxStageK];
+  float* k[kMaxStageK + 1];  // k[j], j < stage: operands; k[stage]: where stage `stage`'s f value goes
+  float a[kMaxStageK + 1][kMaxStageK];  // a[i][j], j < i: row i of the tableau (data dtype)
   const void* dt;     // (B) per-sample step, float or double
-  float* y_out;       // (B,256) or NULL: where y_i is also stored (the last stage's y_i is the step's y1)
+  float* y_out;       // (B,256) or NULL: where y_i of the LAST stage is also stored (the step's y1)
   const int* ctl;     // control block or NULL: the launch is a no-op once the stop flag is set
-  int nk;
+  int stage0, stage1; // 0, 0: plain evaluation of y (no operands)
   int dt_is_f64;
 };
 
@@ -287,10 +292,15 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
     return;
   }
 
+  uint32_t parity = 0;
+  for (int stage = sp.stage0; stage <= sp.stage1; ++stage) {
+  const int nk = stage;                                    // operands k[0 .. nk-1]; 0: plain evaluation of y
+  float* const outp = stage > 0 ? sp.k[stage] : out;       // where this evaluation's result goes
+  float* const y_outp = stage == sp.stage1 ? sp.y_out : nullptr;
   // ---- activation tile: fp32 rows of y -> bf16, swizzled K-major (rows past B are zero) ----
   constexpr int kAChunks = kBM * (kWidth / 8);  // chunks of 8 elements
   constexpr int kAU = kAChunks / kThreads;      // chunks in flight per thread (2 x 16-byte loads each): 8 / 4
-  if (sp.nk > 0) {
+  if (nk > 0) {
     // one 8-element chunk per thread and round; every operand row's two 16-byte loads are issued
     // before the first use (up to 14 loads in flight per thread)
 #pragma unroll 1
@@ -307,7 +317,7 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
         yv[1] = *reinterpret_cast<const float4*>(y + off + 4);
 #pragma unroll
         for (int j = 0; j < kMaxStageK; ++j) {
-          if (j < sp.nk) {
+          if (j < nk) {
             kv[j][0] = *reinterpret_cast<const float4*>(sp.k[j] + off);
             kv[j][1] = *reinterpret_cast<const float4*>(sp.k[j] + off + 4);
           }
@@ -322,18 +332,18 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
             float acc = 0.f;
 #pragma unroll
             for (int j = 0; j < kMaxStageK; ++j) {
-              if (j < sp.nk) {
+              if (j < nk) {
                 const float4 kk = kv[j][h];
                 const float kx = x == 0 ? kk.x : (x == 1 ? kk.y : (x == 2 ? kk.z : kk.w));
-                acc = j == 0 ? __fmul_rn(sp.a[0], kx) : __fmaf_rn(sp.a[j], kx, acc);
+                acc = j == 0 ? __fmul_rn(sp.a[stage][0], kx) : __fmaf_rn(sp.a[stage][j], kx, acc);
               }
             }
             r[h * 4 + x] = __fmaf_rn(dtr, acc, yy[x]);
           }
         }
-        if (sp.y_out != nullptr) {
-          *reinterpret_cast<float4*>(sp.y_out + off) = make_float4(r[0], r[1], r[2], r[3]);
-          *reinterpret_cast<float4*>(sp.y_out + off + 4) = make_float4(r[4], r[5], r[6], r[7]);
+        if (y_outp != nullptr) {
+          *reinterpret_cast<float4*>(y_outp + off) = make_float4(r[0], r[1], r[2], r[3]);
+          *reinterpret_cast<float4*>(y_outp + off + 4) = make_float4(r[4], r[5], r[6], r[7]);
         }
       }
       uint4 p;
@@ -380,7 +390,6 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t idesc = make_idesc(kBM, kWidth);
   const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW), bar = smem_u32(mbar);
-  uint32_t parity = 0;
 
   for (int layer = 0; layer < n_layers; ++layer) {
     // ---- this layer's weights (out, in) = (N, K) row-major -> K-major swizzled, and bias ------
@@ -428,7 +437,7 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
       const float* sOut = reinterpret_cast<const float*>(sW);
       for (int r = warp; r < kBM; r += kThreads / 32) {
         if (m0 + r < B) {
-          float* dst = out + (m0 + r) * kWidth;
+          float* dst = outp + (m0 + r) * kWidth;
 #pragma unroll
           for (int j = 0; j < kWidth / 32; ++j) dst[lane + 32 * j] = sOut[r * kWidth + out_col<kBM>(r, lane + 32 * j)];
         }
@@ -439,13 +448,17 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
     __syncthreads();
     TODE_STAMP();  // epilogue done
   }
+  // next stage of a step-fused launch: its first layer's weights travel while its operand rows are loaded (the
+  // rows k[stage] this CTA just wrote are visible to all its threads after the barrier above)
+  if (stage < sp.stage1) load_weights_async(0);
+  }  // stage
 #ifdef TODE_MLP_TIMING
   if (tid == 0 && blockIdx.x == 0)
     for (int i = 0; i < n_stamp; ++i) reinterpret_cast<long long*>(out)[i] = stamp[i] - stamp[0];
 #endif
 
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -500,7 +513,7 @@ static int launch_mlp(const float* y, const void* weights_bf16, const void* bias
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (sp.nk > 0 && pdl_enabled()) ? 1 : 0;
+  cfg.numAttrs = (sp.stage0 > 0 && pdl_enabled()) ? 1 : 0;
   const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(weights_bf16);
   const float* bias = static_cast<const float*>(biases_f32);
   float* o = static_cast<float*>(out);
@@ -533,14 +546,42 @@ extern "C" int tode_mlp_tanh256_stage_forward(const tode_tableau* tab, int stage
   for (int j = 0; j < stage; ++j) {
     if (!k[j]) return TODE_EINVAL;
     if (reinterpret_cast<uintptr_t>(k[j]) & 15) return TODE_EALIGN;
-    sp.k[j] = static_cast<const float*>(k[j]);
-    sp.a[j] = (float)tab->a[stage][j];  // ButcherTableau.to(data dtype), as tode_erk_stage
+    sp.k[j] = const_cast<float*>(static_cast<const float*>(k[j]));
+    sp.a[stage][j] = (float)tab->a[stage][j];  // ButcherTableau.to(data dtype), as tode_erk_stage
   }
+  if (!out || (reinterpret_cast<uintptr_t>(out) & 15)) return out ? TODE_EALIGN : TODE_EINVAL;
+  sp.k[stage] = static_cast<float*>(out);
   if (y_out && (reinterpret_cast<uintptr_t>(y_out) & 15)) return TODE_EALIGN;
   sp.dt = st->dt;
   sp.y_out = static_cast<float*>(y_out);
   sp.ctl = st->ctl;
-  sp.nk = stage;
+  sp.stage0 = sp.stage1 = stage;
   sp.dt_is_f64 = st->time_dtype == TODE_F64;
   return launch_mlp(static_cast<const float*>(st->y), weights_bf16, biases_f32, out, st->B, n_layers, sp, stream);
+}
+
+extern "C" int tode_mlp_tanh256_step_forward(const tode_tableau* tab, const tode_state* st, void* const* k,
+                                             void* y1_out, const void* weights_bf16, const void* biases_f32,
+                                             int32_t n_layers, void* stream) {
+  using namespace tode::mlp;
+  if (!tab || !st || !k || !st->y || !st->dt) return TODE_EINVAL;
+  if (tab->n_stages < 2 || tab->n_stages - 1 > kMaxStageK) return TODE_ENOSUP;
+  if (st->F != kWidth || st->data_dtype != TODE_F32) return TODE_ENOSUP;
+  if (st->time_dtype != TODE_F32 && st->time_dtype != TODE_F64) return TODE_EINVAL;
+  StageIn sp{};
+  for (int i = 0; i < tab->n_stages; ++i) {
+    if (!k[i]) return TODE_EINVAL;
+    if (reinterpret_cast<uintptr_t>(k[i]) & 15) return TODE_EALIGN;
+    sp.k[i] = static_cast<float*>(k[i]);
+    for (int j = 0; j < i; ++j) sp.a[i][j] = (float)tab->a[i][j];
+  }
+  if (y1_out && (reinterpret_cast<uintptr_t>(y1_out) & 15)) return TODE_EALIGN;
+  sp.dt = st->dt;
+  sp.y_out = static_cast<float*>(y1_out);
+  sp.ctl = st->ctl;
+  sp.stage0 = 1;
+  sp.stage1 = tab->n_stages - 1;
+  sp.dt_is_f64 = st->time_dtype == TODE_F64;
+  return launch_mlp(static_cast<const float*>(st->y), weights_bf16, biases_f32, sp.k[sp.stage1], st->B, n_layers, sp,
+                    stream);
 }
