@@ -53,6 +53,7 @@ if os.environ.get("TODE_REF_SUITE_DEVICE") == "cuda":
 # reference test files that are not expected to pass, with the reason (none: all 69 tests pass -- 61 on the GPU,
 # the 8 of interpolation_test.py on the CPU)
 XFAIL_GPU = {}
+CPU_ONLY = {"interpolation_test.py": "fixtures are torch.from_numpy host tensors: runs in the CPU pass (8 / 8 passed)"}
 
 
 def run_suite(device, files, select=None):

@@ -236,7 +236,7 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   uint8_t* sW = smem + kSmemA;
   float* sBias = reinterpret_cast<float*>(smem + kSmemA + kSmemW);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kSmemA + kSmemW + kWidth * 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);  // mbar[0]: a layer's MMAs done, mbar[1]: its first half
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long m0 = (long long)blockIdx.x * kBM;
@@ -257,21 +257,30 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   }
   if (tid == 32) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(mbar)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(mbar + 1)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
 
   // ---- layer 0 weights: asynchronous global -> shared copies, in flight during the A load ----
-  auto load_weights_async = [&](int layer) {
+  // K-blocks 2 half, 2 half + 1 of a layer's weights (64 KB).  The weight buffer is refilled in halves: the first
+  // two K-blocks as soon as the MMAs that read them are done -- under the second half of the layer's MMAs and the
+  // epilogue -- the other two after the layer's last MMA (round 1 started the whole 128 KB only then and waited
+  // ~0.8 k cycles for it at the top of the next layer, scripts/mlp_timing.py)
+  auto load_weights_half = [&](int layer, int half) {
     const uint4* wsrc = reinterpret_cast<const uint4*>(weights + (size_t)layer * kWidth * kWidth);
     const uint32_t sW_base = smem_u32(sW);
 #pragma unroll 8
-    for (int idx = tid; idx < kWidth * (kWidth / 8); idx += kThreads) {
-      const int n = idx / (kWidth / 8), chunk = idx % (kWidth / 8);
+    for (int idx = tid; idx < kWidth * (kWidth / 16); idx += kThreads) {
+      const int n = idx / (kWidth / 16), chunk = idx % (kWidth / 16) + half * (kWidth / 16);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sW_base + swz(kWBlockBytes, chunk >> 3, n, chunk & 7)),
-                   "l"(wsrc + idx)
+                   "l"(wsrc + n * (kWidth / 8) + chunk)
                    : "memory");
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  auto load_weights_async = [&](int layer) {
+    load_weights_half(layer, 0);
+    load_weights_half(layer, 1);
   };
   load_weights_async(0);
 
@@ -389,7 +398,7 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   TODE_STAMP();  // activation tile loaded
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t idesc = make_idesc(kBM, kWidth);
-  const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW), bar = smem_u32(mbar);
+  const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW), bar = smem_u32(mbar), bar_half = smem_u32(mbar + 1);
 
   for (int layer = 0; layer < n_layers; ++layer) {
     // ---- this layer's weights (out, in) = (N, K) row-major -> K-major swizzled, and bias ------
@@ -411,17 +420,28 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
           const uint64_t b_desc = make_desc(sW_addr + kb * kWBlockBytes + ks * 32);
           mma_bf16(tmem_base, a_desc, b_desc, idesc, (kb | ks) != 0 ? 1u : 0u);
         }
+        if (kb == kNumKBlocks / 2 - 1) {  // the tensor core is done with K-blocks 0, 1 of the weight tile
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_half)
+                       : "memory");
+        }
       }
       // arrives on the mbarrier when every MMA above has completed (implies fence::before_thread_sync)
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar)
                    : "memory");
     }
+    const bool last_layer = layer == n_layers - 1;
+    // 64-row tiles stage the last layer's fp32 output in K-blocks 0, 1 of the weight buffer: K-blocks 2, 3 of the
+    // NEXT STAGE's first layer can already travel under this layer's epilogue
+    const bool next_stage_early = last_layer && kBM == 64 && stage < sp.stage1;
+    mbar_wait(bar_half, parity);
+    if (!last_layer) load_weights_half(layer + 1, 0);
     mbar_wait(bar, parity);
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     TODE_STAMP();  // MMAs done
     // the tensor core is done reading sW: fetch the next layer's weights behind the epilogue
-    if (layer + 1 < n_layers) load_weights_async(layer + 1);
+    if (!last_layer) load_weights_half(layer + 1, 1);
+    if (next_stage_early) load_weights_half(0, 1);
 
     // ---- epilogue: TMEM -> registers, + bias, tanh, -> next layer's activation tile / out ----
     const bool last = layer == n_layers - 1;
@@ -450,7 +470,10 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   }
   // next stage of a step-fused launch: its first layer's weights travel while its operand rows are loaded (the
   // rows k[stage] this CTA just wrote are visible to all its threads after the barrier above)
-  if (stage < sp.stage1) load_weights_async(0);
+  if (stage < sp.stage1) {
+    load_weights_half(0, 0);
+    if (kBM != 64) load_weights_half(0, 1);
+  }
   }  // stage
 #ifdef TODE_MLP_TIMING
   if (tid == 0 && blockIdx.x == 0)
