@@ -1,29 +1,34 @@
 #!/usr/bin/env python
 """Benchmark of the B200-native batch-parallel adaptive RK solve loop.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1..c5] [--impl reference]
 
-One "step" = one complete solve of one batch of synthetic initial value problems through
-the public API (``AutoDiffAdjoint.solve``).  Metric (BASELINE.json): accepted RK steps/s in
-sample-steps (sum of ``stats["n_accepted"]`` / device time), whole job.
+One "step" = one complete solve of one batch of synthetic initial value problems through the public API
+(``AutoDiffAdjoint.solve``).  Metric (BASELINE.json): accepted RK steps/s in sample-steps (sum of
+``stats["n_accepted"]`` / device time), whole job.
 
-Default workload = BASELINE.json ``configs[1]``: Van der Pol mu=10, Tsit5 + PIDController(1e-8,
-1e-8, 0.2, 0.5, 0), batch 2^20 per GPU, dim 2, fp64, t in [0, 20], no t_eval (SURVEY.md 8(d) C2;
-inputs from a CPU ``torch.Generator().manual_seed(1234)``).  For N > 1 (torchrun, one rank
-per GPU) every rank solves its own 2^20-sample slice of an N*2^20 batch (weak scaling, no
-collective in the step loop) and the step ends with the NCCL all-gather of ys / stats.
+Main line = BASELINE.json ``configs[1]``: Van der Pol mu=10, Tsit5 + PIDController(1e-8, 1e-8, 0.2, 0.5, 0), batch
+2^20 per GPU, dim 2, fp64, t in [0, 20], no t_eval (inputs from a CPU
+``torch.Generator().manual_seed(1234 + rank)``).  For N > 1 (torchrun, one rank per GPU) every rank solves its own
+2^20-sample slice (weak scaling, no collective in the step loop) and the step ends with the full-batch Solution on
+every rank (peer stores of the fused kernel into symmetric memory).
 
 The printed JSON line also carries
+  per_config        the other four BASELINE configs in the same run (3 timed steps each): value, ms_per_step,
+                    roofline, route; N > 1: strong scaling of the config's batch, the step ending with the full
+                    Solution on every rank, the shard-only time and the exchange next to it
   roofline          dominant kernel of the workload (algorithmic bytes / event time / measured peak)
-  roofline_kernels  the HBM-bound stage / finish kernels of the stage-wise path, timed live on
-                    2^24 x 2 fp32 operands (each operand 128 MiB > L2)
-  fp64_issue        achieved vs measured double-precision FMA rate (the fused C2 kernel is
-                    fp64-issue-bound, its HBM traffic is 80 B/sample)
-  cpu_baseline      the oracle port (oracle/, OpenMP on the host cores) on a bounded sample
-  e2e               same metric with HOST buffers: H2D of the inputs and D2H of ys + stats inside
-                    the timed region
-``--impl reference`` times the CPU path (the oracle port of the reference; the Python reference
-itself cannot travel to the GPU box) on the host cores and prints the same line shape.
+  roofline_kernels  the HBM-bound stage / finish kernels of the stage-wise path, timed live on 2^24 x 2 fp32
+                    operands (each operand 128 MiB > L2)
+  fp64_issue        achieved vs measured double-precision FMA rate (the fused C2 kernel is fp64-issue-bound)
+  parity_checked    number of samples of the TIMED batch whose counts and ys bits equal the oracle's (rows 0..n-1)
+  cpu_baseline      torchode itself (baseline/_ref, unmodified) eager on the host cores, bounded sample;
+  cpu_baseline_port the oracle port (oracle/, C + OpenMP) on a bounded sample
+  reference_cuda    torchode eager on the SAME GPU on the first 65 536 samples, and the parity of this repo's
+                    result for those samples with it
+  e2e               same metric with HOST buffers: H2D of the inputs and D2H of ys + stats inside the timed region
+``--impl reference`` times the reference itself on the host cores: torch.compile(solver.solve) (compilation
+excluded) if it compiles within its budget, else eager; without baseline/_ref the oracle port (kind "port").
 """
 import argparse
 import ctypes as C
@@ -43,11 +48,6 @@ sys.path.insert(0, ROOT)
 import torchode_b200 as to  # noqa: E402
 from torchode_b200 import _cabi, _launch  # noqa: E402
 from torchode_b200.fields import LinearDecay, LotkaVolterra, VanDerPol  # noqa: E402
-
-# DRAM bytes of the dominant kernel's launch from committed ncu captures, keyed by (workload, batch)
-NCU_DRAM_BYTES = {("c2", 1 << 20): 33709056 + 10891264, ("c3", 1 << 20): 103785216 + 897567232}
-NCU_DRAM_SOURCE = {("c2", 1 << 20): "profiles/r01_ncu_fused_c2_v5.txt (outputs partly still in L2 when the launch ends)",
-                   ("c3", 1 << 20): "profiles/r01_ncu_fused_c3.txt"}
 
 METRIC = "accepted_rk_steps_per_sec"
 UNIT = "sample-steps/s"

@@ -321,6 +321,12 @@ int tode_mlp_tanh256_step_forward(const tode_tableau* tab, const tode_state* st,
                                   void* y1_out, const void* weights_bf16, const void* biases_f32,
                                   int32_t n_layers, void* stream);
 
+/* Multi-GPU (ABI 3): ship `bytes` (multiple of 16) from `src` (this GPU's memory) to n_dst peer buffers
+ * (pointers valid on THIS GPU: peer memory mapped over NVLink) by SM stores -- every vector is read once and
+ * stored to all peers, all links busy at once.  For the dense-output block of a sharded solve (the all-gather
+ * of solutions); the caller's cross-GPU barrier afterwards covers arrival. */
+int tode_peer_push(const void* src, void* const* dst, int32_t n_dst, int64_t bytes, void* stream);
+
 /* Method-of-lines vector field of the 1-D heat equation with Dirichlet ends (configs[4]), one
  * HBM pass: out[b,i] = kappa * ((y[b,i+1] - 2 y[b,i]) + y[b,i-1]) for 0 < i < N-1, 0 at the ends;
  * y, out (B,N) row-major, 16-byte aligned, N divisible by 4 (f32) / 2 (f64).  A user-level f like

@@ -163,6 +163,7 @@ PROTOTYPES = {
     "tode_mlp_tanh256_stage_forward": (C.c_int, [_P(Tableau), C.c_int, _P(State), _P(_vp), _vp, _vp, _vp, _vp,
                                                  C.c_int32, _vp]),
     "tode_mlp_tanh256_step_forward": (C.c_int, [_P(Tableau), _P(State), _P(_vp), _vp, _vp, _vp, C.c_int32, _vp]),
+    "tode_peer_push": (C.c_int, [_vp, _P(_vp), C.c_int32, C.c_int64, _vp]),
     "tode_heat1d_forward": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_double, C.c_int32, _vp]),
     "tode_heat_step": (C.c_int, [_P(Tableau), _P(Controller), _P(State), C.c_double, _vp, _vp, _vp, _vp]),
     "tode_bench_fp64_fma_threads": (C.c_int64, []),

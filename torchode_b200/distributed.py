@@ -146,7 +146,17 @@ class SymmetricWorkspace:
         # ranks every GPU has N - 1 pushes in flight in each direction and the copy engines get 300-340 GB/s per
         # rank (measured at N = 4 and 8), where NCCL's in-place all-gather of the same blocks reaches 590 GB/s:
         # from three ranks on the dense-output block goes through NCCL (profiles/r02_symmetric_8gpu.txt)
-        self.push_by_copy = self.bulk_ys and self.world == 2
+        # ... or through this repo's SM-store push kernel (tode_peer_push: every 16-byte vector read once from
+        # HBM and stored to all peer mappings, every link busy at once); TORCHODE_B200_PUSH = copy | nccl | sm
+        # overrides the choice (experiments)
+        import os
+
+        row_bytes = self.n_points * n_features * esz
+        default = "copy" if self.world == 2 else ("sm" if row_bytes % 16 == 0 else "nccl")
+        self.push_mode = os.environ.get("TORCHODE_B200_PUSH", default) if self.bulk_ys else "none"
+        if self.push_mode == "sm" and row_bytes % 16 != 0:
+            self.push_mode = "nccl"
+        self.push_by_copy = self.push_mode in ("copy", "sm")  # pushes are per row block and need no collective
         self._ys_flat = self.buf[self._off_ys: self._off_ys + G * self.n_points * n_features * esz].view(dtype)
         if self.bulk_ys:
             lo = self.rank * local_batch
@@ -177,6 +187,20 @@ class SymmetricWorkspace:
         ready = torch.cuda.Event()
         ready.record(cur)
         peers = [t for t in self._ys_peer if t is not None]
+        if self.push_mode == "sm":
+            import ctypes as C
+
+            from . import _cabi, _launch
+
+            stream = self._push_streams[0]
+            stream.wait_event(ready)
+            src = self._ys_local[a:b]
+            dst = (C.c_void_p * len(peers))(*[t[a:b].data_ptr() for t in peers])
+            with torch.cuda.stream(stream):
+                _cabi.check(_cabi.lib().tode_peer_push(src.data_ptr(), dst, len(peers),
+                                                       src.numel() * src.element_size(),
+                                                       _launch.stream_ptr(self.buf.device)), "tode_peer_push")
+            return
         for stream, dst in zip(self._push_streams, peers):
             stream.wait_event(ready)
             with torch.cuda.stream(stream):
