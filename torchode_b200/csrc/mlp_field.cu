@@ -17,6 +17,7 @@
 // r % 16, probed with scripts/probes/umma_m64_layout.cu); they are read with tcgen05.ld.16x256b,
 // which spreads 16 lanes over all 32 threads in the mma C-fragment layout (thread l, repeat j:
 // rows l / 4 and l / 4 + 8, columns 8 j + 2 (l % 4) + {0, 1}; scripts/probes/umma_m64_ld16x256b.cu).
+#include <cuda.h>  // CUtensorMap (the driver entry point is resolved at run time: no link against libcuda)
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,6 +25,11 @@
 
 #include "../../include/torchode_b200.h"
 
+// Weight tiles by TMA (cp.async.bulk.tensor, one thread issues two 32 KB boxes per half; the hardware writes the
+// SWIZZLE_128B layout the UMMA descriptors expect and signals an mbarrier) instead of 512 threads x 8 cp.async
+#ifndef TODE_MLP_TMA
+#define TODE_MLP_TMA 1
+#endif
 #ifndef TODE_MLP_PDL_DEFAULT
 #define TODE_MLP_PDL_DEFAULT 0
 #endif
@@ -40,7 +46,7 @@ constexpr int kSmemW = kNumKBlocks * kWBlockBytes;  // 128 KB
 constexpr uint32_t kTmemCols = 256;
 // BM = rows per CTA (UMMA M): the activation tile takes BM * 128 B per K-block
 __host__ __device__ constexpr int smem_a_bytes(int bm) { return kNumKBlocks * bm * 128; }
-__host__ __device__ constexpr int smem_bytes(int bm) { return smem_a_bytes(bm) + kSmemW + kWidth * 4 + 64; }  // + bias + barrier / TMEM slot
+__host__ __device__ constexpr int smem_bytes(int bm) { return smem_a_bytes(bm) + kSmemW + kWidth * 4 + 64; }  // + bias + 3 barriers + TMEM slot
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -71,6 +77,18 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t a_desc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// one box of a tiled tensor map -> shared memory; completion is counted in bytes on `mbar`
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, uint32_t mbar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+          smem_dst),
+      "l"(tmap), "r"(mbar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -226,7 +244,7 @@ template <int kBM>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict__ weights,
                    const float* __restrict__ biases, float* __restrict__ out, long long B, int n_layers,
-                   const __grid_constant__ StageIn sp) {
+                   const __grid_constant__ StageIn sp, const __grid_constant__ CUtensorMap wmap) {
   constexpr int kABlockBytes = kBM * 128;  // per K-block of the activation tile
   constexpr int kSmemA = smem_a_bytes(kBM);
   // 1024-byte alignment (SWIZZLE_128B atoms) is requested from the compiler / driver; no integer
@@ -236,7 +254,8 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   uint8_t* sW = smem + kSmemA;
   float* sBias = reinterpret_cast<float*>(smem + kSmemA + kSmemW);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kSmemA + kSmemW + kWidth * 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);  // mbar[0]: a layer's MMAs done, mbar[1]: its first half
+  // mbar[0]: a layer's MMAs done, mbar[1]: its first half, mbar[2]: a layer's weights have landed (TMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long m0 = (long long)blockIdx.x * kBM;
@@ -255,18 +274,37 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
-  if (tid == 32) {
+  if (tid == 0) {  // the thread that issues the TMA loads and the MMAs
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(mbar)) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(mbar + 1)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;\n" ::"r"(smem_u32(mbar + 2)) : "memory");  // two halves
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+#if TODE_MLP_TMA
+  __syncthreads();  // barriers initialised before the first TMA load is armed on one of them
+#endif
 
   // ---- layer 0 weights: asynchronous global -> shared copies, in flight during the A load ----
   // K-blocks 2 half, 2 half + 1 of a layer's weights (64 KB).  The weight buffer is refilled in halves: the first
   // two K-blocks as soon as the MMAs that read them are done -- under the second half of the layer's MMAs and the
   // epilogue -- the other two after the layer's last MMA (round 1 started the whole 128 KB only then and waited
   // ~0.8 k cycles for it at the top of the next layer, scripts/mlp_timing.py)
-  auto load_weights_half = [&](int layer, int half) {
+#if TODE_MLP_TMA
+  const uint32_t wbar = smem_u32(mbar + 2);
+  uint32_t wparity = 0;
+  // `after_generic`: the destination was last touched by ordinary loads / stores of this CTA (the staged
+  // output tile): order them before the async-proxy writes of the TMA unit
+  auto load_weights_half = [&](int layer, int half, bool after_generic = false) {
+    if (tid == 0) {
+      if (after_generic) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      mbar_arrive_expect_tx(wbar, 2 * kWBlockBytes);
+#pragma unroll
+      for (int kb = 2 * half; kb < 2 * half + 2; ++kb)
+        tma_load_2d(smem_u32(sW) + kb * kWBlockBytes, &wmap, wbar, kb * kKBlock, layer * kWidth);
+    }
+  };
+#else
+  auto load_weights_half = [&](int layer, int half, bool = false) {
     const uint4* wsrc = reinterpret_cast<const uint4*>(weights + (size_t)layer * kWidth * kWidth);
     const uint32_t sW_base = smem_u32(sW);
 #pragma unroll 8
@@ -278,6 +316,7 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   };
+#endif
   auto load_weights_async = [&](int layer) {
     load_weights_half(layer, 0);
     load_weights_half(layer, 1);
@@ -291,6 +330,9 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   asm volatile("griddepcontrol.wait;\n" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if (sp.ctl != nullptr && sp.ctl[TODE_CTL_STOP]) {  // speculative iteration after the stop: undo the prologue
+#if TODE_MLP_TMA
+    if (tid == 0) mbar_wait(wbar, 0);  // the first layer's weights are in flight: shared memory must outlive them
+#endif
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
@@ -408,6 +450,10 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
     // generic-proxy smem writes (cp.async, st.shared) -> visible to the tensor core (async proxy)
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
+#if TODE_MLP_TMA
+    if (tid == 0) mbar_wait(wbar, wparity);  // both halves of this layer's weights have landed
+    wparity ^= 1;
+#endif
     TODE_STAMP();  // this layer's weights have arrived
 
     if (warp == 0 && lane == 0) {
@@ -471,8 +517,8 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   // next stage of a step-fused launch: its first layer's weights travel while its operand rows are loaded (the
   // rows k[stage] this CTA just wrote are visible to all its threads after the barrier above)
   if (stage < sp.stage1) {
-    load_weights_half(0, 0);
-    if (kBM != 64) load_weights_half(0, 1);
+    load_weights_half(0, 0, true);
+    if (kBM != 64) load_weights_half(0, 1, true);
   }
   }  // stage
 #ifdef TODE_MLP_TIMING
@@ -503,6 +549,34 @@ static int launch_error() {
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
+
+#if TODE_MLP_TMA
+// Tiled tensor map over the weights viewed as (n_layers * 256 rows, 256 columns) bf16: boxes of 256 rows x 64
+// columns (one K-block of one layer, 32 KB) land in shared memory in the SWIZZLE_128B layout.  Encoding is a
+// pure host computation (~1 us): done per launch, nothing cached, nothing to go stale.
+static int weight_tensor_map(const void* weights_bf16, int n_layers, CUtensorMap* map) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  if (encode == nullptr) return TODE_ENOSUP;
+  const cuuint64_t dims[2] = {(cuuint64_t)kWidth, (cuuint64_t)kWidth * (cuuint64_t)n_layers};
+  const cuuint64_t strides[1] = {(cuuint64_t)kWidth * 2};  // bytes between rows
+  const cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)kWidth};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(weights_bf16), dims, strides,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : TODE_EINVAL;
+}
+#endif
 
 static int launch_mlp(const float* y, const void* weights_bf16, const void* biases_f32, void* out, int64_t B,
                       int32_t n_layers, const StageIn& sp, void* stream) {
@@ -542,8 +616,12 @@ static int launch_mlp(const float* y, const void* weights_bf16, const void* bias
   float* o = static_cast<float*>(out);
   const long long rows = (long long)B;
   const int layers = (int)n_layers;
-  const cudaError_t e = big ? cudaLaunchKernelEx(&cfg, mlp_tanh256_kernel<128>, y, w, bias, o, rows, layers, sp)
-                            : cudaLaunchKernelEx(&cfg, mlp_tanh256_kernel<64>, y, w, bias, o, rows, layers, sp);
+  CUtensorMap wmap{};
+#if TODE_MLP_TMA
+  if (const int rc = weight_tensor_map(weights_bf16, layers, &wmap)) return rc;
+#endif
+  const cudaError_t e = big ? cudaLaunchKernelEx(&cfg, mlp_tanh256_kernel<128>, y, w, bias, o, rows, layers, sp, wmap)
+                            : cudaLaunchKernelEx(&cfg, mlp_tanh256_kernel<64>, y, w, bias, o, rows, layers, sp, wmap);
   if (e != cudaSuccess) return (int)e;
   return launch_error();
 }
