@@ -870,6 +870,22 @@ def run_workload(env, name, batch, steps, warmup, *, main, extras):
         "roofline": roofline, "route": last_run, "steps": steps, "warmup": warmup,
         "gpu_launches": int(last_run.get("kernel_launches", last_run.get("kernel_launches_min", 0))) * steps,
     }
+    if name == "c3" and fused:
+        # the dense-output kernel is bound by instruction issue, not HBM: its issue-slot
+        # utilisation next to the HBM figure.  Warp instructions per sample are a property of kernel + workload
+        # read off the committed ncu capture (661.4 M for 2^20 samples, profiles/r02_ncu_f2_final.txt), not measured live
+        sm_clock = 1.965e9
+        props = torch.cuda.get_device_properties(device)
+        instr = 630.7 * B
+        res["issue_slots"] = {
+            "bound": "issue", "warp_instr_per_sample": 630.7,
+            "warp_instr_source": "static: profiles/r02_ncu_f2_final.txt (smsp__inst_executed.sum / samples)",
+            "achieved_ginstr_per_s": instr / (kernel_ms * 1e-3) / 1e9,
+            "peak_ginstr_per_s": props.multi_processor_count * 4 * sm_clock / 1e9,
+            "frac": instr / (kernel_ms * 1e-3) / (props.multi_processor_count * 4 * sm_clock),
+            "active_lanes_per_instr": 20.8,
+            "note": "peak = SMs x 4 schedulers x 1.965 GHz; 20.8 of 32 lanes active (t_eval loop: a warp takes as many "
+                    "trips as its busiest lane has points)"}
     if name == "c3":
         res["config"]["rows_redrawn"] = redrawn
         res["config"]["rows_redrawn_why"] = ("samples whose solve ends in INFINITE_NORM (fp32 overflow in an over-long "
