@@ -365,6 +365,11 @@ int tode_bench_fp64_fma(int64_t iters, void* sink, int64_t* n_fma_out, void* str
  * on the device, zeroed by the caller; [0..3] receive the number of mismatches per function,
  * [4..7] how often the fast flag stayed set. */
 int tode_selftest_fast_math(int64_t n, uint64_t seed, const tode_controller* ctrl, void* counts8, void* stream);
+/* Test aid: the fp32 fast-path division / square root of the packed kernels (erk_fused_f2.cuh: div_fast,
+ * div_fast2, sqrt_fast) against div.rn.f32 / sqrt.rn.f32 on n pseudo-random and adversarial operands;
+ * counts6 = device uint64[6] (zeroed by the caller): [0..2] mismatches (division, division by sqrt(2),
+ * square root) where the range flag is set, [3..5] how often it was set. */
+int tode_selftest_fast_math_f32(int64_t n, uint64_t seed, void* counts6, void* stream);
 
 #ifdef __cplusplus
 }

@@ -159,3 +159,22 @@ def test_f2_kernel_equals_oracle(field_name, method, ctrl):
     assert sol.stats["n_initialized"].cpu().numpy().tolist() == ref["n_initialized"].tolist()
     assert int(sol.stats["n_f_evals"][0]) == int(ref["n_f_evals"])
     assert bits_equal(sol.ys.cpu().numpy(), ref["ys"])
+
+
+def test_f32_fast_division_and_sqrt_are_bit_identical_to_the_ieee_instructions():
+    """div_fast / div_fast2 / rcp_refined2 / sqrt_fast (erk_fused_f2.cuh, also used by heat_step.cu) against
+    div.rn.f32 / sqrt.rn.f32 wherever their range flag is set: 2^28 operand triples -- a third any bit pattern,
+    a third in the solver's range, a third around the limits of the flags (2^-60, 2^60, 2^-101, zeros,
+    subnormals, near-overflow)."""
+    import ctypes as C
+
+    from torchode_b200 import _launch
+
+    counts = torch.zeros(6, dtype=torch.int64, device=DEV)
+    n = 1 << 28
+    _cabi.check(_cabi.lib().tode_selftest_fast_math_f32(n, 20261017, counts.data_ptr(),
+                                                        _launch.stream_ptr(counts.device)), "selftest f32")
+    got = counts.tolist()
+    assert got[:3] == [0, 0, 0], f"mismatches (division, division by sqrt(2), square root): {got[:3]}"
+    # the flags must leave the fast path open for the solver's range (a third of the operands) and more
+    assert got[3] > n // 4 and got[4] > n // 3 and got[5] > n // 2, got

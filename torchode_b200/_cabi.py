@@ -169,6 +169,7 @@ PROTOTYPES = {
     "tode_bench_fp64_fma_threads": (C.c_int64, []),
     "tode_bench_fp64_fma": (C.c_int, [C.c_int64, _vp, _P(C.c_int64), _vp]),
     "tode_selftest_fast_math": (C.c_int, [C.c_int64, C.c_uint64, _P(Controller), _vp, _vp]),
+    "tode_selftest_fast_math_f32": (C.c_int, [C.c_int64, C.c_uint64, _vp, _vp]),
     "tode_adapt_step_size": (
         C.c_int,
         [_P(Controller), C.c_int32, C.c_int32, C.c_int64, C.c_int64] + [_vp] * 12 + [_vp],

@@ -3,6 +3,7 @@
 // with the checked ones on pseudo-random and adversarial operands: wherever the fast
 // function leaves its range flag set, the two must agree bit for bit.
 #include "api_common.cuh"
+#include "erk_fused_f2.cuh"  // the fp32 fast-path division / square root of the packed kernels
 
 namespace tode {
 namespace {
@@ -134,5 +135,88 @@ extern "C" int tode_selftest_fast_math(int64_t n, uint64_t seed, const tode_cont
   const tode::CtrlP<double, double> c = tode::make_ctrl<double, double>(ctrl);
   tode::selftest_kernel<<<tode::sm_count() * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       (long long)n, (unsigned long long)seed, c, tode::make_powtab(), static_cast<unsigned long long*>(counts8));
+  return tode::launch_status();
+}
+
+// ---- fp32: div_fast / div_fast2 / sqrt_fast of erk_fused_f2.cuh against div.rn.f32 / sqrt.rn.f32 ------------
+namespace tode {
+namespace {
+
+__device__ float gen32(unsigned long long h, int mode) {
+  const unsigned int w = (unsigned int)(h >> 17);
+  if (mode == 0) return __uint_as_float(w);  // any bit pattern
+  const unsigned int mant = w & 0x007fffffu, sign = w & 0x80000000u;
+  if (mode == 1) return __uint_as_float(sign | ((127u - 30u + (unsigned int)((h >> 8) % 60)) << 23) | mant);  // the solver's range
+  // around the limits of mid_range ([2^-60, 2^60]) and of sqrt's fast path (2^-101), zeros, subnormals
+  switch ((unsigned int)(h & 7)) {
+    case 0: return __uint_as_float(sign);
+    case 1: return __uint_as_float(sign | mant);
+    case 2: return __uint_as_float(sign | ((127u - 61u + (unsigned int)((h >> 8) % 3)) << 23) | mant);
+    case 3: return __uint_as_float(sign | ((127u + 59u + (unsigned int)((h >> 8) % 3)) << 23) | mant);
+    case 4: return __uint_as_float(((127u - 102u + (unsigned int)((h >> 8) % 3)) << 23) | mant);
+    case 5: return __uint_as_float(sign | (0x7f000000u) | mant);
+    case 6: return __uint_as_float(sign | 0x3f800000u | (mant & 3));
+    default: return __uint_as_float(sign | ((1u + (unsigned int)((h >> 8) % 253)) << 23) | mant);
+  }
+}
+
+// counts[0..2]: mismatches of division (scalar and packed, shared reciprocal) / division by sqrt(2) / square
+// root; counts[3..5]: how often the fast path's range flag was set
+__global__ void selftest_f32_kernel(long long n, unsigned long long seed, unsigned long long* counts) {
+  unsigned long long bad[3] = {0, 0, 0}, used[3] = {0, 0, 0};
+  const float sqrt2 = (float)sqrt(2.0), r_sqrt2 = rcp_refined(sqrt2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long h0 = mix64(seed + 3 * (unsigned long long)i), h1 = mix64(h0), h2 = mix64(h1);
+    const int mode = (int)(i % 3);
+    const float a = gen32(h0, mode), b = gen32(h1, mode), a2 = gen32(h2, mode);
+    if (mid_range(b)) {
+      const float r = rcp_refined(b);
+      if (mid_range(a) || a == 0.0f) {  // (the kernels pass |err| or a positive time difference: +0, never -0)
+        used[0]++;
+        const float fa = a == 0.0f ? 0.0f : a;
+        if (__float_as_uint(div_fast(fa, b, r)) != __float_as_uint(__fdiv_rn(fa, b))) bad[0]++;
+      }
+      if (mid_range(a) && mid_range(a2)) {  // two numerators, one divisor (the t_eval loop), packed
+        const float2 q = div_fast2(make_float2(a, a2), splat(b), splat(r));
+        if (__float_as_uint(q.x) != __float_as_uint(__fdiv_rn(a, b)) ||
+            __float_as_uint(q.y) != __float_as_uint(__fdiv_rn(a2, b)))
+          bad[0]++;
+      }
+      if (mid_range(a) && mid_range(a2)) {  // two divisions with their own divisors (|err| / bounds), packed
+        const float b2 = fabsf(a2);
+        const float2 q = div_fast2(make_float2(fabsf(a), fabsf(b)), make_float2(fabsf(b), b2),
+                                   rcp_refined2(make_float2(fabsf(b), b2)));
+        if (__float_as_uint(q.x) != __float_as_uint(__fdiv_rn(fabsf(a), fabsf(b))) ||
+            __float_as_uint(q.y) != __float_as_uint(__fdiv_rn(fabsf(b), b2)))
+          bad[0]++;
+      }
+    }
+    if (mid_range(a)) {
+      used[1]++;
+      if (__float_as_uint(div_fast(a, sqrt2, r_sqrt2)) != __float_as_uint(__fdiv_rn(a, sqrt2))) bad[1]++;
+    }
+    {
+      const float x = fabsf(a);
+      bool ok = true;
+      const float s = sqrt_fast(x, ok);
+      if (ok) {
+        used[2]++;
+        if (__float_as_uint(s) != __float_as_uint(__fsqrt_rn(x))) bad[2]++;
+      }
+    }
+  }
+  for (int j = 0; j < 3; ++j) {
+    if (bad[j]) atomicAdd(&counts[j], bad[j]);
+    if (used[j]) atomicAdd(&counts[3 + j], used[j]);
+  }
+}
+
+}  // namespace
+}  // namespace tode
+
+extern "C" int tode_selftest_fast_math_f32(int64_t n, uint64_t seed, void* counts6, void* stream) {
+  if (n <= 0 || !counts6) return TODE_EINVAL;
+  tode::selftest_f32_kernel<<<tode::sm_count() * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (long long)n, (unsigned long long)seed, static_cast<unsigned long long*>(counts6));
   return tode::launch_status();
 }
