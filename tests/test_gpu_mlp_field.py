@@ -120,12 +120,13 @@ def test_stage_fused_evaluation_equals_stage_kernel_then_field(B, tdtype, method
     assert (got == 7.0).all()
 
 
-@pytest.mark.parametrize("B", [700, 8192, 19000])  # 19000: 128-row tiles
+@pytest.mark.parametrize("B,n_layers", [(700, 3), (8192, 3), (19000, 3), (1000, 1), (1000, 2), (37, 4)])  # 19000: 128-row tiles
 @pytest.mark.parametrize("method", [to.Dopri5, to.Tsit5])
-def test_all_stages_in_one_launch_equal_one_launch_per_stage(B, method):
-    """tode_mlp_tanh256_step_forward (round 2: a CTA walks the six stages of its rows) against six
-    tode_mlp_tanh256_stage_forward launches: same bits in every k_i, y1 and the whole solve."""
-    field = make_field(3)
+def test_all_stages_in_one_launch_equal_one_launch_per_stage(B, n_layers, method):
+    """tode_mlp_tanh256_step_forward (round 2: a CTA walks the six stages of its rows; with 64-row tiles the
+    operand rows come from partial sums formed under the previous stage's MMAs -- scheduled by layer, hence the
+    layer counts) against six tode_mlp_tanh256_stage_forward launches: same bits in every k_i, y1 and the solve."""
+    field = make_field(n_layers)
     g = torch.Generator().manual_seed(B)
     problem = to.InitialValueProblem(torch.randn(B, 256, generator=g).to(DEV), torch.zeros(B, device=DEV),
                                      (0.3 + 0.4 * torch.rand(B, generator=g)).to(DEV))

@@ -46,7 +46,13 @@ constexpr int kSmemW = kNumKBlocks * kWBlockBytes;  // 128 KB
 constexpr uint32_t kTmemCols = 256;
 // BM = rows per CTA (UMMA M): the activation tile takes BM * 128 B per K-block
 __host__ __device__ constexpr int smem_a_bytes(int bm) { return kNumKBlocks * bm * 128; }
-__host__ __device__ constexpr int smem_bytes(int bm) { return smem_a_bytes(bm) + kSmemW + kWidth * 4 + 64; }  // + bias + 3 barriers + TMEM slot
+constexpr int kMaxLayers = 8;
+// behind the two tiles: BM = 128 keeps every layer's bias (8 KB); BM = 64 keeps the fp32 partial stage sum of the
+// NEXT stage's operand rows (64 x 256 fp32 = 64 KB, step-fused launches) and reads its biases into registers
+constexpr int kBiasBytes = kMaxLayers * kWidth * 4;
+constexpr int kPartialBytes = 64 * kWidth * 4;
+__host__ __device__ constexpr int smem_extra_bytes(int bm) { return bm == 64 ? kPartialBytes : kBiasBytes; }
+__host__ __device__ constexpr int smem_bytes(int bm) { return smem_a_bytes(bm) + kSmemW + smem_extra_bytes(bm) + 64; }  // + 3 barriers + TMEM slot
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -117,11 +123,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // physical column of logical column `col` of row `row` in the staged fp32 output tile: a
 // per-row permutation that makes both the epilogue's writes and the row-wise copy-out
 // conflict-free (BM = 128: one row per lane -> XOR with the row; BM = 64: the C-fragment layout
-// has 8 rows x 4 column pairs per instruction -> rotation by 8 (row % 4) + (row / 4) % 2)
+// has 8 rows x 4 column pairs per instruction: 8-byte stores, a half-warp = 4 rows x 4 pairs -> rotation by
+// 8 (row % 4) columns, which keeps 4-column groups together for the 16-byte reads of the copy-out)
 template <int BM>
 __device__ __forceinline__ int out_col(int row, int col) {
   if (BM == 128) return col ^ (row & 31);
-  return (col + 8 * (row & 3) + ((row >> 2) & 1)) & (kWidth - 1);
+  return (col + 8 * (row & 3)) & (kWidth - 1);
 }
 
 __device__ __forceinline__ float bias_act(uint32_t acc, float bias, bool last) {
@@ -180,7 +187,8 @@ __device__ __forceinline__ void epilogue_m128(uint32_t tmem_base, uint8_t* sA, u
 // BM = 64: rows 16 q .. 16 q + 15 sit in lanes 0..15 of subpartition q; 16x256b.x8 hands thread
 // `lane` the rows lane / 4 (+ 8) and, per repeat j, the column pair 8 j + 2 (lane % 4) + {0, 1}
 // of this warp's 64 columns: 32 elements per thread, all 32 threads busy
-__device__ __forceinline__ void epilogue_m64(uint32_t tmem_base, uint8_t* sA, uint8_t* sW, const float* sBias,
+// `bia[j]`: the bias of this thread's column pair of repeat j (loaded from global memory before the MMA wait)
+__device__ __forceinline__ void epilogue_m64(uint32_t tmem_base, uint8_t* sA, uint8_t* sW, const float2* bia,
                                              int q, int cq, int lane, bool last) {
   constexpr int kABlockBytes = 64 * 128;
   uint32_t r[32];
@@ -201,7 +209,7 @@ __device__ __forceinline__ void epilogue_m64(uint32_t tmem_base, uint8_t* sA, ui
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int col = cq * 64 + 8 * j + cpair;  // and col + 1
-    const float b0 = sBias[col], b1 = sBias[col + 1];
+    const float b0 = bia[j].x, b1 = bia[j].y;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int row = row_lo + 8 * h;
@@ -211,8 +219,7 @@ __device__ __forceinline__ void epilogue_m64(uint32_t tmem_base, uint8_t* sA, ui
         *reinterpret_cast<uint32_t*>(sA + swz(kABlockBytes, cq, row, j) + 2 * cpair) = pack_bf16(v0, v1);
       } else {
         float* sOut = reinterpret_cast<float*>(sW);
-        sOut[row * kWidth + out_col<64>(row, col)] = v0;
-        sOut[row * kWidth + out_col<64>(row, col + 1)] = v1;
+        *reinterpret_cast<float2*>(sOut + row * kWidth + out_col<64>(row, col)) = make_float2(v0, v1);
       }
     }
   }
@@ -240,7 +247,26 @@ struct StageIn {
   int dt_is_f64;
 };
 
-template <int kBM>
+// acc[0..8) = a[row][0] k_0, then fma(a[row][j], k_j, acc) for j < N, of the 8 elements at `off`: all 2 N loads first
+template <int N>
+__device__ __forceinline__ void partial_chunk(const StageIn& sp, int a_row, size_t off, float* acc) {
+  float4 kv[N][2];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    kv[j][0] = *reinterpret_cast<const float4*>(sp.k[j] + off);
+    kv[j][1] = *reinterpret_cast<const float4*>(sp.k[j] + off + 4);
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const float a = sp.a[a_row][j];
+    const float kk[8] = {kv[j][0].x, kv[j][0].y, kv[j][0].z, kv[j][0].w, kv[j][1].x, kv[j][1].y, kv[j][1].z, kv[j][1].w};
+#pragma unroll
+    for (int x = 0; x < 8; ++x) acc[x] = j == 0 ? __fmul_rn(a, kk[x]) : __fmaf_rn(a, kk[x], acc[x]);
+  }
+}
+
+// kStep (BM = 64 only): the launch covers stages 1 .. stage1 > 1 of a step -- operand rows through the partial sums
+template <int kBM, bool kStep>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict__ weights,
                    const float* __restrict__ biases, float* __restrict__ out, long long B, int n_layers,
@@ -252,8 +278,9 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = smem + kSmemA;
-  float* sBias = reinterpret_cast<float*>(smem + kSmemA + kSmemW);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kSmemA + kSmemW + kWidth * 4);
+  float* sBias = reinterpret_cast<float*>(smem + kSmemA + kSmemW);    // BM = 128
+  float4* sP = reinterpret_cast<float4*>(smem + kSmemA + kSmemW);     // BM = 64: [round][half][thread]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kSmemA + kSmemW + smem_extra_bytes(kBM));
   // mbar[0]: a layer's MMAs done, mbar[1]: its first half, mbar[2]: a layer's weights have landed (TMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 3);
 
@@ -262,7 +289,8 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
 #ifdef TODE_MLP_TIMING
   long long stamp[16];
   int n_stamp = 0;
-#define TODE_STAMP() do { if (tid == 0 && n_stamp < 16) stamp[n_stamp++] = clock64(); } while (0)
+  int stamp_stage = 0;  // -DTODE_MLP_TIMING=<first stage whose phases are stamped>
+#define TODE_STAMP() do { if (tid == 0 && n_stamp < 16 && (n_stamp == 0 || stamp_stage >= TODE_MLP_TIMING)) stamp[n_stamp++] = clock64(); } while (0)
 #else
 #define TODE_STAMP() do { } while (0)
 #endif
@@ -322,6 +350,11 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
     load_weights_half(layer, 1);
   };
   load_weights_async(0);
+  // every layer's bias, once (round 2: the per-layer load sat, with its full L2 latency, between a layer's epilogue
+  // and the next layer's first MMA: ~0.6 k cycles per layer, scripts/mlp_timing.py)
+  if constexpr (kBM == 128) {
+    for (int idx = tid; idx < n_layers * kWidth; idx += kThreads) sBias[idx] = biases[idx];
+  }
 
   // Everything above is independent of the kernel launched before this one (TMEM allocation,
   // barrier, the first layer's weights): under programmatic dependent launch it overlaps that
@@ -345,13 +378,80 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
 
   uint32_t parity = 0;
   for (int stage = sp.stage0; stage <= sp.stage1; ++stage) {
+#ifdef TODE_MLP_TIMING
+  stamp_stage = stage;
+  TODE_STAMP();  // stage begins
+#endif
   const int nk = stage;                                    // operands k[0 .. nk-1]; 0: plain evaluation of y
   float* const outp = stage > 0 ? sp.k[stage] : out;       // where this evaluation's result goes
   float* const y_outp = stage == sp.stage1 ? sp.y_out : nullptr;
   // ---- activation tile: fp32 rows of y -> bf16, swizzled K-major (rows past B are zero) ----
   constexpr int kAChunks = kBM * (kWidth / 8);  // chunks of 8 elements
   constexpr int kAU = kAChunks / kThreads;      // chunks in flight per thread (2 x 16-byte loads each): 8 / 4
-  if (nk > 0) {
+  // BM = 64, step-fused: all operands but the newest were summed under the previous stage's MMAs (sP, see
+  // partial_round below); y and k[nk-1] of all four rounds are requested at once -- one L2 round trip per stage
+  // instead of four with up to 14 loads each.  Same chain: P = a_0 k_0, fma(a_j, k_j, P) ascending j, the newest
+  // operand last, then fma(dt, acc, y).
+  if (kStep && nk > 0) {  // (stage0 == 1: the first stage has one operand, every later one finds its partial sum)
+    constexpr int kRounds = 2;  // of kAChunks / kThreads = 4 at a time: 8 x 16-byte loads in flight per thread
+    const float* knew = sp.k[nk - 1];
+    const float a_new = sp.a[stage][nk - 1];
+#pragma unroll 1
+    for (int r0 = 0; r0 < kAChunks / kThreads; r0 += kRounds) {
+    float4 yv[kRounds][2], kv[kRounds][2];
+    float dtr[kRounds];
+#pragma unroll
+    for (int rr = 0; rr < kRounds; ++rr) {
+      const int r = r0 + rr;
+      const int idx = r * kThreads + tid;
+      const int row = idx / (kWidth / 8), chunk = idx % (kWidth / 8);
+      if (m0 + row < B) {
+        const size_t off = (size_t)(m0 + row) * kWidth + chunk * 8;
+        yv[rr][0] = *reinterpret_cast<const float4*>(y + off);
+        yv[rr][1] = *reinterpret_cast<const float4*>(y + off + 4);
+        kv[rr][0] = *reinterpret_cast<const float4*>(knew + off);
+        kv[rr][1] = *reinterpret_cast<const float4*>(knew + off + 4);
+        dtr[rr] = sp.dt_is_f64 ? (float)static_cast<const double*>(sp.dt)[m0 + row]
+                               : static_cast<const float*>(sp.dt)[m0 + row];
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < kRounds; ++rr) {
+      const int r = r0 + rr;
+      const int idx = r * kThreads + tid;
+      const int row = idx / (kWidth / 8), chunk = idx % (kWidth / 8);
+      float res[8];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) res[x] = 0.f;
+      if (m0 + row < B) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (nk > 1) pp = sP[(r * 2 + h) * kThreads + tid];
+          const float yy[4] = {yv[rr][h].x, yv[rr][h].y, yv[rr][h].z, yv[rr][h].w};
+          const float kk[4] = {kv[rr][h].x, kv[rr][h].y, kv[rr][h].z, kv[rr][h].w};
+          const float pa[4] = {pp.x, pp.y, pp.z, pp.w};
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const float acc = nk == 1 ? __fmul_rn(a_new, kk[x]) : __fmaf_rn(a_new, kk[x], pa[x]);
+            res[h * 4 + x] = __fmaf_rn(dtr[rr], acc, yy[x]);
+          }
+        }
+        if (y_outp != nullptr) {
+          const size_t off = (size_t)(m0 + row) * kWidth + chunk * 8;
+          *reinterpret_cast<float4*>(y_outp + off) = make_float4(res[0], res[1], res[2], res[3]);
+          *reinterpret_cast<float4*>(y_outp + off + 4) = make_float4(res[4], res[5], res[6], res[7]);
+        }
+      }
+      uint4 p;
+      p.x = pack_bf16(res[0], res[1]);
+      p.y = pack_bf16(res[2], res[3]);
+      p.z = pack_bf16(res[4], res[5]);
+      p.w = pack_bf16(res[6], res[7]);
+      *reinterpret_cast<uint4*>(sA + swz(kABlockBytes, chunk >> 3, row, chunk & 7)) = p;
+    }
+    }
+  } else if (!kStep && nk > 0) {
     // one 8-element chunk per thread and round; every operand row's two 16-byte loads are issued
     // before the first use (up to 14 loads in flight per thread)
 #pragma unroll 1
@@ -434,6 +534,8 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   }
   }
 
+  // generic-proxy smem writes (st.shared) -> visible to the tensor core (async proxy)
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -442,17 +544,42 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   const uint32_t idesc = make_idesc(kBM, kWidth);
   const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW), bar = smem_u32(mbar), bar_half = smem_u32(mbar + 1);
 
+  // Round `r` (512 chunks of 8 elements) of the NEXT stage's partial operand sum, run by the threads while they
+  // would otherwise wait for this stage's MMAs: P = a[s+1][0] k_0, fma(a[s+1][j], k_j, P) for j < s (all of them
+  // written before this stage began; k_s itself joins when the next stage forms its rows).  Every thread reads
+  // back only what it wrote: no barrier.
+  const bool do_partial = kStep && stage >= 1 && stage < sp.stage1;
+  auto partial_round = [&](int r) {
+    const int idx = r * kThreads + tid;
+    const int row = idx / (kWidth / 8), chunk = idx % (kWidth / 8);
+    float acc[8];
+#pragma unroll
+    for (int x = 0; x < 8; ++x) acc[x] = 0.f;
+    if (m0 + row < B) {
+      const size_t off = (size_t)(m0 + row) * kWidth + chunk * 8;
+      switch (stage) {  // one fully unrolled body per operand count: everything stays in registers
+        case 1: partial_chunk<1>(sp, stage + 1, off, acc); break;
+        case 2: partial_chunk<2>(sp, stage + 1, off, acc); break;
+        case 3: partial_chunk<3>(sp, stage + 1, off, acc); break;
+        case 4: partial_chunk<4>(sp, stage + 1, off, acc); break;
+        default: partial_chunk<5>(sp, stage + 1, off, acc); break;
+      }
+    }
+    sP[(r * 2 + 0) * kThreads + tid] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    sP[(r * 2 + 1) * kThreads + tid] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  };
+
   for (int layer = 0; layer < n_layers; ++layer) {
     // ---- this layer's weights (out, in) = (N, K) row-major -> K-major swizzled, and bias ------
     // (issued right after the previous layer's MMAs completed, in flight during its epilogue)
-    if (tid < kWidth) sBias[tid] = biases[layer * kWidth + tid];
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
-    // generic-proxy smem writes (cp.async, st.shared) -> visible to the tensor core (async proxy)
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    __syncthreads();
+    // (the activation tile is complete and fenced: barrier after the operand rows / the previous epilogue)
 #if TODE_MLP_TMA
     if (tid == 0) mbar_wait(wbar, wparity);  // both halves of this layer's weights have landed
     wparity ^= 1;
+#else
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
 #endif
     TODE_STAMP();  // this layer's weights have arrived
 
@@ -479,8 +606,32 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
     // 64-row tiles stage the last layer's fp32 output in K-blocks 0, 1 of the weight buffer: K-blocks 2, 3 of the
     // NEXT STAGE's first layer can already travel under this layer's epilogue
     const bool next_stage_early = last_layer && kBM == 64 && stage < sp.stage1;
+    // rounds of the next stage's partial sum under this layer's MMAs: layer 0 takes 0, 1 (all four if it is the only
+    // layer), layer 1 takes 2, 3; the first of them before the half-way barrier
+    int pr = 4, pr_end = 4;
+    if (kStep && do_partial && layer < 2) {
+      pr = 2 * layer;
+      pr_end = n_layers == 1 ? 4 : pr + 2;
+      partial_round(pr++);
+    }
     mbar_wait(bar_half, parity);
     if (!last_layer) load_weights_half(layer + 1, 0);
+    if constexpr (kStep) {
+#pragma unroll 1
+      for (; pr < pr_end; ++pr) partial_round(pr);
+    }
+    // BM = 64: this thread's 16 bias values of the layer travel under the MMAs
+    // (the epilogue's thread coordinates come from a laundered copy of tid: its ~40 loop-invariant addresses are
+    // then formed here, per layer, instead of living in registers across the operand rows and the partial rounds)
+    int tid_e = tid;
+    asm volatile("" : "+r"(tid_e));
+    const int warp_e = tid_e >> 5, lane_e = tid_e & 31;
+    float2 bia[8];
+    if constexpr (kBM == 64) {
+      const float2* bg = reinterpret_cast<const float2*>(biases + layer * kWidth + (warp_e >> 2) * 64 + 2 * (lane_e & 3));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bia[j] = bg[4 * j];
+    }
     mbar_wait(bar, parity);
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -491,11 +642,11 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
 
     // ---- epilogue: TMEM -> registers, + bias, tanh, -> next layer's activation tile / out ----
     const bool last = layer == n_layers - 1;
-    const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter
+    const int q = warp_e & 3, cq = warp_e >> 2;  // TMEM lane quarter, column quarter
     if constexpr (kBM == 128) {
-      epilogue_m128(tmem_base, sA, sW, sBias, q, cq, lane, last);
+      epilogue_m128(tmem_base, sA, sW, sBias + layer * kWidth, q, cq, lane_e, last);
     } else {
-      epilogue_m64(tmem_base, sA, sW, sBias, q, cq, lane, last);
+      epilogue_m64(tmem_base, sA, sW, bia, q, cq, lane_e, last);
     }
     if (last) {
       __syncthreads();
@@ -504,12 +655,22 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
       for (int r = warp; r < kBM; r += kThreads / 32) {
         if (m0 + r < B) {
           float* dst = outp + (m0 + r) * kWidth;
+          if constexpr (kBM == 64) {  // the row's rotation keeps 4-column groups: 16-byte reads and stores
 #pragma unroll
-          for (int j = 0; j < kWidth / 32; ++j) dst[lane + 32 * j] = sOut[r * kWidth + out_col<kBM>(r, lane + 32 * j)];
+            for (int j = 0; j < kWidth / 128; ++j) {
+              const int col = 4 * (lane + 32 * j);
+              *reinterpret_cast<float4*>(dst + col) =
+                  *reinterpret_cast<const float4*>(sOut + r * kWidth + out_col<64>(r, col));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < kWidth / 32; ++j) dst[lane + 32 * j] = sOut[r * kWidth + out_col<kBM>(r, lane + 32 * j)];
+          }
         }
       }
     }
     // TMEM reads and smem writes of this layer are done before the next layer's MMA starts
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     TODE_STAMP();  // epilogue done
@@ -524,6 +685,7 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
 #ifdef TODE_MLP_TIMING
   if (tid == 0 && blockIdx.x == 0)
     for (int i = 0; i < n_stamp; ++i) reinterpret_cast<long long*>(out)[i] = stamp[i] - stamp[0];
+  if (tid == 0 && blockIdx.x == 0) reinterpret_cast<long long*>(out)[n_stamp] = -1;
 #endif
 
   if (warp == 0) {
@@ -580,16 +742,18 @@ static int weight_tensor_map(const void* weights_bf16, int n_layers, CUtensorMap
 
 static int launch_mlp(const float* y, const void* weights_bf16, const void* biases_f32, void* out, int64_t B,
                       int32_t n_layers, const StageIn& sp, void* stream) {
-  if (!y || !weights_bf16 || !biases_f32 || !out || n_layers < 1 || n_layers > 8) return TODE_EINVAL;
+  if (!y || !weights_bf16 || !biases_f32 || !out || n_layers < 1 || n_layers > kMaxLayers) return TODE_EINVAL;
   if (B == 0) return 0;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (!al16(y) || !al16(weights_bf16) || !al16(out)) return TODE_EALIGN;
+  if (!al16(y) || !al16(weights_bf16) || !al16(out) || !al16(biases_f32)) return TODE_EALIGN;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_tanh256_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(mlp_tanh256_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_bytes(128));
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(mlp_tanh256_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(64));
+      e = cudaFuncSetAttribute(mlp_tanh256_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(64));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mlp_tanh256_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(64));
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
@@ -620,8 +784,10 @@ static int launch_mlp(const float* y, const void* weights_bf16, const void* bias
 #if TODE_MLP_TMA
   if (const int rc = weight_tensor_map(weights_bf16, layers, &wmap)) return rc;
 #endif
-  const cudaError_t e = big ? cudaLaunchKernelEx(&cfg, mlp_tanh256_kernel<128>, y, w, bias, o, rows, layers, sp, wmap)
-                            : cudaLaunchKernelEx(&cfg, mlp_tanh256_kernel<64>, y, w, bias, o, rows, layers, sp, wmap);
+  const bool step = !big && sp.stage0 == 1 && sp.stage1 > 1;
+  const cudaError_t e = big ? cudaLaunchKernelEx(&cfg, mlp_tanh256_kernel<128, false>, y, w, bias, o, rows, layers, sp, wmap)
+                        : step ? cudaLaunchKernelEx(&cfg, mlp_tanh256_kernel<64, true>, y, w, bias, o, rows, layers, sp, wmap)
+                               : cudaLaunchKernelEx(&cfg, mlp_tanh256_kernel<64, false>, y, w, bias, o, rows, layers, sp, wmap);
   if (e != cudaSuccess) return (int)e;
   return launch_error();
 }
