@@ -25,11 +25,8 @@
 
 #include "../../include/torchode_b200.h"
 
-// Weight tiles by TMA (cp.async.bulk.tensor, one thread issues two 32 KB boxes per half; the hardware writes the
-// SWIZZLE_128B layout the UMMA descriptors expect and signals an mbarrier) instead of 512 threads x 8 cp.async
-#ifndef TODE_MLP_TMA
-#define TODE_MLP_TMA 1
-#endif
+// Weight tiles travel by TMA (cp.async.bulk.tensor, one thread issues two 32 KB boxes per half; the hardware writes
+// the SWIZZLE_128B layout the UMMA descriptors expect and signals an mbarrier; round 1 used 512 threads x 8 cp.async)
 #ifndef TODE_MLP_PDL_DEFAULT
 #define TODE_MLP_PDL_DEFAULT 0
 #endif
@@ -43,7 +40,8 @@ constexpr int kKBlock = 64;                    // bf16 elements per 128-byte swi
 constexpr int kNumKBlocks = kWidth / kKBlock;  // 4
 constexpr int kWBlockBytes = kWidth * 128;     // 32 KB per K-block of the weight tile
 constexpr int kSmemW = kNumKBlocks * kWBlockBytes;  // 128 KB
-constexpr uint32_t kTmemCols = 256;
+// TMEM columns: the accumulator (256); step-fused launches keep the fp32 y tile of the step in 128 more
+__host__ __device__ constexpr uint32_t tmem_cols(bool step) { return step ? 512u : 256u; }
 // BM = rows per CTA (UMMA M): the activation tile takes BM * 128 B per K-block
 __host__ __device__ constexpr int smem_a_bytes(int bm) { return kNumKBlocks * bm * 128; }
 constexpr int kMaxLayers = 8;
@@ -107,6 +105,34 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!ok);
+}
+
+// 32 consecutive columns of this thread's TMEM lane <-> 32 registers
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+        "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
 }
 
 // byte offset of the 16-byte chunk holding elements [8c, 8c+8) of K-block kb of `row`
@@ -281,8 +307,13 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   float* sBias = reinterpret_cast<float*>(smem + kSmemA + kSmemW);    // BM = 128
   float4* sP = reinterpret_cast<float4*>(smem + kSmemA + kSmemW);     // BM = 64: [round][half][thread]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kSmemA + kSmemW + smem_extra_bytes(kBM));
-  // mbar[0]: a layer's MMAs done, mbar[1]: its first half, mbar[2]: a layer's weights have landed (TMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 3);
+  // mbar[0]: a layer's MMAs done, mbar[1]: its first half, mbar[2], mbar[3]: K-blocks 0-1 / 2-3 of a layer's weights
+  // have landed (TMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 4);
+  constexpr uint32_t kTmemCols = tmem_cols(kStep);
+  // step-fused: the staged fp32 output tile (64 KB) sits in K-blocks 2-3 of the weight buffer, where the next stage
+  // reads its newest operand from; K-blocks 0-1 take the next stage's first weights meanwhile
+  uint8_t* const sOutTile = sW + (kStep ? 2 * kWBlockBytes : 0);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long m0 = (long long)blockIdx.x * kBM;
@@ -305,46 +336,35 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   if (tid == 0) {  // the thread that issues the TMA loads and the MMAs
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(mbar)) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(mbar + 1)) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;\n" ::"r"(smem_u32(mbar + 2)) : "memory");  // two halves
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(mbar + 2)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(mbar + 3)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-#if TODE_MLP_TMA
-  __syncthreads();  // barriers initialised before the first TMA load is armed on one of them
-#endif
+  // barriers initialised before the first TMA load is armed on one of them; the TMEM address is published
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
 
   // ---- layer 0 weights: asynchronous global -> shared copies, in flight during the A load ----
   // K-blocks 2 half, 2 half + 1 of a layer's weights (64 KB).  The weight buffer is refilled in halves: the first
   // two K-blocks as soon as the MMAs that read them are done -- under the second half of the layer's MMAs and the
   // epilogue -- the other two after the layer's last MMA (round 1 started the whole 128 KB only then and waited
   // ~0.8 k cycles for it at the top of the next layer, scripts/mlp_timing.py)
-#if TODE_MLP_TMA
-  const uint32_t wbar = smem_u32(mbar + 2);
+  const uint32_t wbar0 = smem_u32(mbar + 2), wbar1 = smem_u32(mbar + 3);
   uint32_t wparity = 0;
   // `after_generic`: the destination was last touched by ordinary loads / stores of this CTA (the staged
   // output tile): order them before the async-proxy writes of the TMA unit
   auto load_weights_half = [&](int layer, int half, bool after_generic = false) {
     if (tid == 0) {
       if (after_generic) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      const uint32_t wbar = half ? wbar1 : wbar0;
       mbar_arrive_expect_tx(wbar, 2 * kWBlockBytes);
 #pragma unroll
       for (int kb = 2 * half; kb < 2 * half + 2; ++kb)
         tma_load_2d(smem_u32(sW) + kb * kWBlockBytes, &wmap, wbar, kb * kKBlock, layer * kWidth);
     }
   };
-#else
-  auto load_weights_half = [&](int layer, int half, bool = false) {
-    const uint4* wsrc = reinterpret_cast<const uint4*>(weights + (size_t)layer * kWidth * kWidth);
-    const uint32_t sW_base = smem_u32(sW);
-#pragma unroll 8
-    for (int idx = tid; idx < kWidth * (kWidth / 16); idx += kThreads) {
-      const int n = idx / (kWidth / 16), chunk = idx % (kWidth / 16) + half * (kWidth / 16);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sW_base + swz(kWBlockBytes, chunk >> 3, n, chunk & 7)),
-                   "l"(wsrc + n * (kWidth / 8) + chunk)
-                   : "memory");
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-  };
-#endif
   auto load_weights_async = [&](int layer) {
     load_weights_half(layer, 0);
     load_weights_half(layer, 1);
@@ -363,17 +383,42 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   asm volatile("griddepcontrol.wait;\n" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if (sp.ctl != nullptr && sp.ctl[TODE_CTL_STOP]) {  // speculative iteration after the stop: undo the prologue
-#if TODE_MLP_TMA
-    if (tid == 0) mbar_wait(wbar, 0);  // the first layer's weights are in flight: shared memory must outlive them
-#endif
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    if (tid == 0) {  // the first layer's weights are in flight: shared memory must outlive them
+      mbar_wait(wbar0, 0);
+      mbar_wait(wbar1, 0);
+    }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     if (warp == 0) {
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
     return;
+  }
+
+  // ---- step-fused: the step's y tile goes to TMEM once (32 columns of this thread's lane = its four 8-element
+  // chunks), the rows' dt to registers; every stage of the step forms its rows from them
+  const uint32_t y_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256u + 32u * (uint32_t)(warp >> 2);
+  float dtr[4] = {0.f, 0.f, 0.f, 0.f};
+  if constexpr (kStep) {
+    uint32_t yr[32];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = r * (kThreads / 32) + warp;
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      if (m0 + row < B) {
+        const float4* src = reinterpret_cast<const float4*>(y + (m0 + row) * kWidth + lane * 8);
+        v0 = src[0];
+        v1 = src[1];
+        dtr[r] = sp.dt_is_f64 ? (float)static_cast<const double*>(sp.dt)[m0 + row]
+                              : static_cast<const float*>(sp.dt)[m0 + row];
+      }
+      yr[r * 8 + 0] = __float_as_uint(v0.x), yr[r * 8 + 1] = __float_as_uint(v0.y);
+      yr[r * 8 + 2] = __float_as_uint(v0.z), yr[r * 8 + 3] = __float_as_uint(v0.w);
+      yr[r * 8 + 4] = __float_as_uint(v1.x), yr[r * 8 + 5] = __float_as_uint(v1.y);
+      yr[r * 8 + 6] = __float_as_uint(v1.z), yr[r * 8 + 7] = __float_as_uint(v1.w);
+    }
+    tmem_st_32x32b_x32(y_taddr, yr);
   }
 
   uint32_t parity = 0;
@@ -388,38 +433,41 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   // ---- activation tile: fp32 rows of y -> bf16, swizzled K-major (rows past B are zero) ----
   constexpr int kAChunks = kBM * (kWidth / 8);  // chunks of 8 elements
   constexpr int kAU = kAChunks / kThreads;      // chunks in flight per thread (2 x 16-byte loads each): 8 / 4
-  // BM = 64, step-fused: all operands but the newest were summed under the previous stage's MMAs (sP, see
-  // partial_round below); y and k[nk-1] of all four rounds are requested at once -- one L2 round trip per stage
-  // instead of four with up to 14 loads each.  Same chain: P = a_0 k_0, fma(a_j, k_j, P) ascending j, the newest
-  // operand last, then fma(dt, acc, y).
-  if (kStep && nk > 0) {  // (stage0 == 1: the first stage has one operand, every later one finds its partial sum)
-    constexpr int kRounds = 2;  // of kAChunks / kThreads = 4 at a time: 8 x 16-byte loads in flight per thread
-    const float* knew = sp.k[nk - 1];
+  // BM = 64, step-fused: no global loads on the way into a stage.  All operands but the newest were summed under the
+  // previous stage's MMAs (sP, see partial_round below), the newest, k[nk-1], is still in the staged output tile of
+  // the evaluation that produced it, y sits in TMEM, dt in registers.  (The first stage of the launch reads k[0],
+  // which a previous launch produced, from global memory.)  Same chain: P = a_0 k_0, fma(a_j, k_j, P) ascending j,
+  // the newest operand last, then fma(dt, acc, y).
+  if (kStep && nk > 0) {
+    constexpr int kRounds = kAChunks / kThreads;  // 4
     const float a_new = sp.a[stage][nk - 1];
-#pragma unroll 1
-    for (int r0 = 0; r0 < kAChunks / kThreads; r0 += kRounds) {
-    float4 yv[kRounds][2], kv[kRounds][2];
-    float dtr[kRounds];
+    float4 kv[kRounds][2];
+    if (nk == 1) {
 #pragma unroll
-    for (int rr = 0; rr < kRounds; ++rr) {
-      const int r = r0 + rr;
-      const int idx = r * kThreads + tid;
-      const int row = idx / (kWidth / 8), chunk = idx % (kWidth / 8);
-      if (m0 + row < B) {
-        const size_t off = (size_t)(m0 + row) * kWidth + chunk * 8;
-        yv[rr][0] = *reinterpret_cast<const float4*>(y + off);
-        yv[rr][1] = *reinterpret_cast<const float4*>(y + off + 4);
-        kv[rr][0] = *reinterpret_cast<const float4*>(knew + off);
-        kv[rr][1] = *reinterpret_cast<const float4*>(knew + off + 4);
-        dtr[rr] = sp.dt_is_f64 ? (float)static_cast<const double*>(sp.dt)[m0 + row]
-                               : static_cast<const float*>(sp.dt)[m0 + row];
+      for (int r = 0; r < kRounds; ++r) {
+        const int row = r * (kThreads / 32) + warp;
+        kv[r][0] = kv[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + row < B) {
+          const float4* src = reinterpret_cast<const float4*>(sp.k[0] + (m0 + row) * kWidth + lane * 8);
+          kv[r][0] = src[0];
+          kv[r][1] = src[1];
+        }
+      }
+    } else {
+      const float* sOut = reinterpret_cast<const float*>(sOutTile);
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int row = r * (kThreads / 32) + warp;
+        const float4* src = reinterpret_cast<const float4*>(sOut + row * kWidth + out_col<64>(row, lane * 8));
+        kv[r][0] = src[0];
+        kv[r][1] = src[1];
       }
     }
+    uint32_t yr[32];
+    tmem_ld_32x32b_x32(y_taddr, yr);
 #pragma unroll
-    for (int rr = 0; rr < kRounds; ++rr) {
-      const int r = r0 + rr;
-      const int idx = r * kThreads + tid;
-      const int row = idx / (kWidth / 8), chunk = idx % (kWidth / 8);
+    for (int r = 0; r < kRounds; ++r) {
+      const int row = r * (kThreads / 32) + warp, chunk = lane;
       float res[8];
 #pragma unroll
       for (int x = 0; x < 8; ++x) res[x] = 0.f;
@@ -428,13 +476,12 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
         for (int h = 0; h < 2; ++h) {
           float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
           if (nk > 1) pp = sP[(r * 2 + h) * kThreads + tid];
-          const float yy[4] = {yv[rr][h].x, yv[rr][h].y, yv[rr][h].z, yv[rr][h].w};
-          const float kk[4] = {kv[rr][h].x, kv[rr][h].y, kv[rr][h].z, kv[rr][h].w};
+          const float kk[4] = {kv[r][h].x, kv[r][h].y, kv[r][h].z, kv[r][h].w};
           const float pa[4] = {pp.x, pp.y, pp.z, pp.w};
 #pragma unroll
           for (int x = 0; x < 4; ++x) {
             const float acc = nk == 1 ? __fmul_rn(a_new, kk[x]) : __fmaf_rn(a_new, kk[x], pa[x]);
-            res[h * 4 + x] = __fmaf_rn(dtr[rr], acc, yy[x]);
+            res[h * 4 + x] = __fmaf_rn(dtr[r], acc, __uint_as_float(yr[r * 8 + h * 4 + x]));
           }
         }
         if (y_outp != nullptr) {
@@ -449,7 +496,6 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
       p.z = pack_bf16(res[4], res[5]);
       p.w = pack_bf16(res[6], res[7]);
       *reinterpret_cast<uint4*>(sA + swz(kABlockBytes, chunk >> 3, row, chunk & 7)) = p;
-    }
     }
   } else if (!kStep && nk > 0) {
     // one 8-element chunk per thread and round; every operand row's two 16-byte loads are issued
@@ -540,7 +586,9 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   TODE_STAMP();  // activation tile loaded
-  const uint32_t tmem_base = *tmem_slot;
+  // step-fused, later stages: the staged output tile has been read; K-blocks 2-3 of this stage's first layer take
+  // its place (they are needed half-way through the layer's MMAs)
+  if (kStep && stage > sp.stage0) load_weights_half(0, 1, true);
   const uint32_t idesc = make_idesc(kBM, kWidth);
   const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW), bar = smem_u32(mbar), bar_half = smem_u32(mbar + 1);
 
@@ -573,20 +621,13 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
     // ---- this layer's weights (out, in) = (N, K) row-major -> K-major swizzled, and bias ------
     // (issued right after the previous layer's MMAs completed, in flight during its epilogue)
     // (the activation tile is complete and fenced: barrier after the operand rows / the previous epilogue)
-#if TODE_MLP_TMA
-    if (tid == 0) mbar_wait(wbar, wparity);  // both halves of this layer's weights have landed
-    wparity ^= 1;
-#else
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    __syncthreads();
-#endif
-    TODE_STAMP();  // this layer's weights have arrived
-
     if (warp == 0 && lane == 0) {
+      mbar_wait(wbar0, wparity);  // K-blocks 0-1 of this layer's weights have landed
+      TODE_STAMP();               // (first half of) this layer's weights have arrived
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
       for (int kb = 0; kb < kNumKBlocks; ++kb) {
+        if (kb == kNumKBlocks / 2) mbar_wait(wbar1, wparity);  // K-blocks 2-3
 #pragma unroll
         for (int ks = 0; ks < kKBlock / 16; ++ks) {
           const uint64_t a_desc = make_desc(sA_addr + kb * kABlockBytes + ks * 32);
@@ -602,20 +643,28 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar)
                    : "memory");
     }
+    wparity ^= 1;
     const bool last_layer = layer == n_layers - 1;
-    // 64-row tiles stage the last layer's fp32 output in K-blocks 0, 1 of the weight buffer: K-blocks 2, 3 of the
-    // NEXT STAGE's first layer can already travel under this layer's epilogue
-    const bool next_stage_early = last_layer && kBM == 64 && stage < sp.stage1;
-    // rounds of the next stage's partial sum under this layer's MMAs: layer 0 takes 0, 1 (all four if it is the only
-    // layer), layer 1 takes 2, 3; the first of them before the half-way barrier
+    // step-fused: the last layer's output tile is staged in K-blocks 2-3, so K-blocks 0-1 of the NEXT STAGE's first
+    // layer can travel as soon as this layer's MMAs are done with theirs
+    const bool next_stage_early = kStep && last_layer && stage < sp.stage1;
+    // rounds of the next stage's partial sum under this layer's MMAs (L2 -> SM bandwidth bounds them: ~2.4 k cycles
+    // each with the weights streaming beside them): one each under layers 0 and 1, two under layer 2, where no next
+    // layer's weights travel (1 layer: all four; 2 layers: two each); the first of them before the half-way barrier
     int pr = 4, pr_end = 4;
-    if (kStep && do_partial && layer < 2) {
-      pr = 2 * layer;
-      pr_end = n_layers == 1 ? 4 : pr + 2;
-      partial_round(pr++);
+    if (kStep && do_partial && layer < 3) {
+      if (n_layers == 1) {
+        pr = 0, pr_end = 4;
+      } else if (n_layers == 2) {
+        pr = 2 * layer, pr_end = layer < 2 ? pr + 2 : pr;
+      } else {
+        pr = layer, pr_end = layer == 2 ? 4 : layer + 1;
+      }
+      if (pr < pr_end) partial_round(pr++);
     }
     mbar_wait(bar_half, parity);
     if (!last_layer) load_weights_half(layer + 1, 0);
+    if (next_stage_early) load_weights_half(0, 0);
     if constexpr (kStep) {
 #pragma unroll 1
       for (; pr < pr_end; ++pr) partial_round(pr);
@@ -638,7 +687,6 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
     TODE_STAMP();  // MMAs done
     // the tensor core is done reading sW: fetch the next layer's weights behind the epilogue
     if (!last_layer) load_weights_half(layer + 1, 1);
-    if (next_stage_early) load_weights_half(0, 1);
 
     // ---- epilogue: TMEM -> registers, + bias, tanh, -> next layer's activation tile / out ----
     const bool last = layer == n_layers - 1;
@@ -646,12 +694,12 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
     if constexpr (kBM == 128) {
       epilogue_m128(tmem_base, sA, sW, sBias + layer * kWidth, q, cq, lane_e, last);
     } else {
-      epilogue_m64(tmem_base, sA, sW, bia, q, cq, lane_e, last);
+      epilogue_m64(tmem_base, sA, sOutTile, bia, q, cq, lane_e, last);
     }
     if (last) {
       __syncthreads();
       // coalesced copy-out: one warp writes whole 1 KB rows, 128 contiguous bytes per instruction
-      const float* sOut = reinterpret_cast<const float*>(sW);
+      const float* sOut = reinterpret_cast<const float*>(sOutTile);
       for (int r = warp; r < kBM; r += kThreads / 32) {
         if (m0 + r < B) {
           float* dst = outp + (m0 + r) * kWidth;
@@ -675,11 +723,11 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
     __syncthreads();
     TODE_STAMP();  // epilogue done
   }
-  // next stage of a step-fused launch: its first layer's weights travel while its operand rows are loaded (the
-  // rows k[stage] this CTA just wrote are visible to all its threads after the barrier above)
-  if (stage < sp.stage1) {
+  // next stage of a multi-stage launch with 128-row tiles (the output tile took the whole weight buffer): its first
+  // layer's weights travel while its operand rows are loaded
+  if (!kStep && stage < sp.stage1) {
     load_weights_half(0, 0, true);
-    if (kBM != 64) load_weights_half(0, 1, true);
+    load_weights_half(0, 1, true);
   }
   }  // stage
 #ifdef TODE_MLP_TIMING
@@ -689,7 +737,7 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
 #endif
 
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(*tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -712,7 +760,6 @@ static int launch_error() {
   return e == cudaSuccess ? 0 : (int)e;
 }
 
-#if TODE_MLP_TMA
 // Tiled tensor map over the weights viewed as (n_layers * 256 rows, 256 columns) bf16: boxes of 256 rows x 64
 // columns (one K-block of one layer, 32 KB) land in shared memory in the SWIZZLE_128B layout.  Encoding is a
 // pure host computation (~1 us): done per launch, nothing cached, nothing to go stale.
@@ -738,7 +785,6 @@ static int weight_tensor_map(const void* weights_bf16, int n_layers, CUtensorMap
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : TODE_EINVAL;
 }
-#endif
 
 static int launch_mlp(const float* y, const void* weights_bf16, const void* biases_f32, void* out, int64_t B,
                       int32_t n_layers, const StageIn& sp, void* stream) {
@@ -781,9 +827,7 @@ static int launch_mlp(const float* y, const void* weights_bf16, const void* bias
   const long long rows = (long long)B;
   const int layers = (int)n_layers;
   CUtensorMap wmap{};
-#if TODE_MLP_TMA
   if (const int rc = weight_tensor_map(weights_bf16, layers, &wmap)) return rc;
-#endif
   const bool step = !big && sp.stage0 == 1 && sp.stage1 > 1;
   const cudaError_t e = big ? cudaLaunchKernelEx(&cfg, mlp_tanh256_kernel<128, false>, y, w, bias, o, rows, layers, sp, wmap)
                         : step ? cudaLaunchKernelEx(&cfg, mlp_tanh256_kernel<64, true>, y, w, bias, o, rows, layers, sp, wmap)
