@@ -53,6 +53,10 @@ def test_heat_step_kernel_keeps_its_unfused_products():
 
 
 def test_tensor_core_and_tmem_instructions_are_in_the_mlp_kernel():
-    sass = "\n".join(sass_of("mlp_field.o", r"_ZN4tode3mlp18mlp_tanh256_kernelILi(64|128)EE"))
+    sass = "\n".join(sass_of("mlp_field.o", r"_ZN4tode3mlp18mlp_tanh256_kernelILi(64|128)ELb[01]EE"))
     for op in ("UTCHMMA", "LDTM", "UTCBAR", "UTMALDG"):  # tcgen05.mma, tcgen05.ld, tcgen05.commit, TMA tile loads
         assert count(sass, op) > 0, op
+    # the step-fused instantiation keeps the step's y tile in TMEM (tcgen05.st) and has no local-memory traffic
+    step = "\n".join(sass_of("mlp_field.o", r"_ZN4tode3mlp18mlp_tanh256_kernelILi64ELb1EE"))
+    assert count(step, "STTM") > 0
+    assert count(step, "STL") == 0 and count(step, "LDL") == 0
