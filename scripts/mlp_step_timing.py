@@ -43,6 +43,14 @@ print(f"B={B}: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us per step launch (6 evalua
 if "timing" in os.environ.get("TORCHODE_B200_LIB", ""):
     stamps = ks[6][0].view(torch.int64)[:17].tolist()
     n = stamps.index(-1) if -1 in stamps else 16
+    if "_op" in os.environ["TORCHODE_B200_LIB"]:  # -DTODE_MLP_TIMING_OPERAND=<thread>: extra stamps in the operand phase
+        names = ["kernel start", "stage begins", "newest operand read", "y read (TMEM)", "rows formed + stored",
+                 "proxy fence", "barrier"] + ["(layer phases; 'weights in' only for thread 0)"] * 10
+        prev = 0
+        for name, s_ in zip(names, stamps[:n]):
+            print(f"{name:28s} {s_:8d} cycles  (+{s_ - prev})")
+            prev = s_
+        sys.exit(0)
     names = ["kernel start", "stage begins", "operand rows formed"] + [x for l in range(3) for x in (
         f"L{l} weights in", f"L{l} MMA done", f"L{l} epilogue done")] + ["next stage begins"] + ["..."] * 8
     prev = 0

@@ -1,5 +1,5 @@
 """Phase timestamps (SM clock cycles, CTA 0) of the tcgen05 MLP field: needs a library built with
--DTODE_MLP_TIMING (TORCHODE_B200_LIB=build_variants/mlp_timing.so)."""
+-DTODE_MLP_TIMING=0 (stamps from stage 0 on, i.e. the plain evaluation; TORCHODE_B200_LIB=build_variants/mlp_timing.so)."""
 import sys
 import torch
 sys.path.insert(0, ".")

@@ -322,8 +322,16 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   int n_stamp = 0;
   int stamp_stage = 0;  // -DTODE_MLP_TIMING=<first stage whose phases are stamped>
 #define TODE_STAMP() do { if (tid == 0 && n_stamp < 16 && (n_stamp == 0 || stamp_stage >= TODE_MLP_TIMING)) stamp[n_stamp++] = clock64(); } while (0)
+#ifdef TODE_MLP_TIMING_OPERAND  // extra stamps inside the operand phase, all taken by thread TODE_MLP_TIMING_OPERAND
+#undef TODE_STAMP
+#define TODE_STAMP() do { if (tid == TODE_MLP_TIMING_OPERAND && n_stamp < 16 && (n_stamp == 0 || stamp_stage >= TODE_MLP_TIMING)) stamp[n_stamp++] = clock64(); } while (0)
+#define TODE_STAMP_X() TODE_STAMP()
+#else
+#define TODE_STAMP_X() do { } while (0)
+#endif
 #else
 #define TODE_STAMP() do { } while (0)
+#define TODE_STAMP_X() do { } while (0)
 #endif
   TODE_STAMP();
 
@@ -463,8 +471,10 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
         kv[r][1] = src[1];
       }
     }
+    TODE_STAMP_X();  // newest operand read
     uint32_t yr[32];
     tmem_ld_32x32b_x32(y_taddr, yr);
+    TODE_STAMP_X();  // y read
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
       const int row = r * (kThreads / 32) + warp, chunk = lane;
@@ -580,8 +590,10 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   }
   }
 
+  TODE_STAMP_X();  // rows formed and stored
   // generic-proxy smem writes (st.shared) -> visible to the tensor core (async proxy)
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  TODE_STAMP_X();  // fenced
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -731,9 +743,16 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
   }
   }  // stage
 #ifdef TODE_MLP_TIMING
-  if (tid == 0 && blockIdx.x == 0)
+#ifdef TODE_MLP_TIMING_OPERAND
+  const int stamp_tid = TODE_MLP_TIMING_OPERAND;
+#else
+  const int stamp_tid = 0;
+#endif
+  __syncthreads();
+  if (tid == stamp_tid && blockIdx.x == 0) {
     for (int i = 0; i < n_stamp; ++i) reinterpret_cast<long long*>(out)[i] = stamp[i] - stamp[0];
-  if (tid == 0 && blockIdx.x == 0) reinterpret_cast<long long*>(out)[n_stamp] = -1;
+    reinterpret_cast<long long*>(out)[n_stamp] = -1;
+  }
 #endif
 
   if (warp == 0) {
