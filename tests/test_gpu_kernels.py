@@ -774,6 +774,35 @@ def test_solve_from_host_equals_the_device_solve(kind):
 
 
 @pytest.mark.parametrize("with_t_eval", [False, True])
+def test_solve_from_host_cuts_few_wide_rows_by_bytes(with_t_eval):
+    """configs[4] in miniature: 12 rows of a method-of-lines grid (kernel-backed field: the solve drives its loop from
+    the host).  By sample count that is one chunk; ``min_chunk_bytes`` cuts it so that the copies of the other
+    chunks run under a chunk's solve -- all copy-ins are queued first, each chunk's results leave on its own
+    stream.  Same bits as one device solve."""
+    from torchode_b200.fields import Heat1D
+
+    B, F = 12, 4096
+    g = torch.Generator().manual_seed(3)
+    x = torch.linspace(0, 1, F)
+    y0 = (torch.sin(torch.pi * x)[None] * (1 + torch.rand(B, 1, generator=g))).pin_memory()
+    t_eval = torch.linspace(0, 2e-6, 5).expand(B, -1) if with_t_eval else None
+    host = to.InitialValueProblem(y0, torch.zeros(B).pin_memory(), torch.full((B,), 2e-6).pin_memory(), t_eval)
+    term = to.ODETerm(Heat1D(1.0 / (x[1] - x[0]).item() ** 2))
+    solver = to.AutoDiffAdjoint(to.Tsit5(term), to.IntegralController(1e-6, 1e-4, term=term))
+    want = solver.solve(to.InitialValueProblem(y0.cuda(), host.t_start.cuda(), host.t_end.cuda(),
+                                               None if t_eval is None else t_eval.cuda()))
+    one = to.solve_from_host(solver, host, "cuda")  # 12 samples, 0.2-1 MB moved: not worth a second stream
+    assert solver.last_run["chunks"] == 1
+    got = to.solve_from_host(solver, host, "cuda", chunks=5, min_chunk_bytes=64 << 10, out=one)
+    assert solver.last_run["chunks"] == 5
+    for sol in (one, got):
+        assert sol.ys.is_pinned() and bits_equal(sol.ys.numpy(), want.ys.cpu().numpy())
+        assert sol.status.tolist() == want.status.tolist() and (sol.status == 0).all()
+        for k in ("n_steps", "n_accepted", "n_initialized"):
+            assert sol.stats[k].tolist() == want.stats[k].tolist(), k
+
+
+@pytest.mark.parametrize("with_t_eval", [False, True])
 def test_fused_kernel_writes_replicas_of_the_gathered_buffers(with_t_eval):
     """tode_solution.peer_*: the multi-GPU "write the all-gather while solving" path, exercised on
     one GPU with two replicas that both live here (on a box they are peer mappings over NVLink)."""

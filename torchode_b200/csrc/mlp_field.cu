@@ -466,9 +466,13 @@ mlp_tanh256_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict_
 #pragma unroll
       for (int r = 0; r < kRounds; ++r) {
         const int row = r * (kThreads / 32) + warp;
+        // (lanes 4-7 of every 8 take their second half first: the eight 16-byte loads of a quarter-warp then fall
+        // into eight different bank groups instead of four)
         const float4* src = reinterpret_cast<const float4*>(sOut + row * kWidth + out_col<64>(row, lane * 8));
-        kv[r][0] = src[0];
-        kv[r][1] = src[1];
+        const int swap = (lane >> 2) & 1;
+        const float4 a = src[swap], b = src[swap ^ 1];
+        kv[r][0] = swap ? b : a;
+        kv[r][1] = swap ? a : b;
       }
     }
     TODE_STAMP_X();  // newest operand read

@@ -27,19 +27,25 @@ def _pinned_like(shape, dtype) -> torch.Tensor:
 
 
 def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, device, *, chunks: int = 8,
-                    min_chunk: int = 4096, dt0: Optional[torch.Tensor] = None, args: Any = None,
-                    out: Optional[Solution] = None) -> Solution:
+                    min_chunk: int = 4096, min_chunk_bytes: int = 256 << 20, dt0: Optional[torch.Tensor] = None,
+                    args: Any = None, out: Optional[Solution] = None) -> Solution:
     """``problem``: an InitialValueProblem over CPU tensors (pinned memory makes the copies
     asynchronous).  Returns a Solution over pinned CPU tensors.  ``out``: the Solution of an earlier
     call with the same shapes, whose buffers are reused (allocating pinned memory costs more than a
-    solve).  ``min_chunk``: smallest chunk worth a stream of its own (small batches are launch-bound:
-    they run as one chunk)."""
+    solve).  A chunk is worth a stream of its own if it has ``min_chunk`` samples (small batches of narrow
+    states are launch-bound: they run as one chunk) OR moves ``min_chunk_bytes`` over PCIe (few wide samples --
+    64 x 4 MB rows of a method-of-lines grid -- are cut by bytes: their copies are what there is to hide).  The
+    default of 256 MB per chunk is what configs[4] measures (scripts/c5_e2e_chunks.py, 268 MB each way, B200):
+    22.2 ms in one piece, 20.8 ms in two, 22.4 in four, 27.2 in eight -- a chunk whose solve drives its loop from the
+    host pays that loop's latency again, which eats what the hidden copies give beyond two chunks."""
     device = torch.device(device)
     term_ = solver.step_method.term
     assert term_ is not None, "solve_from_host needs the ODE term on the step method"
     B, F, Tn = problem.batch_size, problem.n_features, problem.n_evaluation_points
     D = problem.data_dtype
-    chunks = max(1, min(int(chunks), B // max(1, int(min_chunk)))) if B else 1
+    moved = B * F * (1 + max(Tn, 1)) * torch.empty((), dtype=D).element_size()  # y0 in, ys out
+    worth = max(B // max(1, int(min_chunk)), moved // max(1, int(min_chunk_bytes)))
+    chunks = max(1, min(int(chunks), worth, B)) if B else 1
     bounds = [shard_bounds(B, i, chunks) for i in range(chunks)]
     reuse = (out is not None and out.ys.shape == (B, max(Tn, 1), F) and out.ys.dtype == D
              and out.ys.is_pinned() and out.status.shape == (B,))
@@ -66,18 +72,29 @@ def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, devic
         te_dev_row = te_host[:1].to(device, non_blocking=True) if te_broadcast else None
         ready = torch.cuda.Event()
         ready.record()
+        # every chunk's copy-in is queued before the first solve: a chunk whose solve drives its loop from the
+        # host (opaque f, the kernel-backed fields) would otherwise hold back the copies of all later chunks
+        staged = []
         for i, (lo, hi) in enumerate(bounds):
             with torch.cuda.stream(streams[i]):
                 streams[i].wait_event(ready)
                 t_eval = te_dev_row.expand(hi - lo, -1) if te_broadcast else to_dev(te_host, lo, hi)
-                prob_i = InitialValueProblem(to_dev(problem.y0, lo, hi), to_dev(problem.t_start, lo, hi),
-                                             to_dev(problem.t_end, lo, hi), t_eval)
-                dt0_i = to_dev(dt0, lo, hi)
+                staged.append((InitialValueProblem(to_dev(problem.y0, lo, hi), to_dev(problem.t_start, lo, hi),
+                                                   to_dev(problem.t_end, lo, hi), t_eval), to_dev(dt0, lo, hi)))
+        for i, (lo, hi) in enumerate(bounds):
+            with torch.cuda.stream(streams[i]):
+                prob_i, dt0_i = staged[i]
                 field = solver._fused_eligible(prob_i, term_) if hi > lo else None
                 if field is None:
-                    # opaque f / plug-ins / empty chunk: the solve synchronises with the host itself
+                    # opaque f / plug-ins / empty chunk: the solve synchronises with the host itself; its results
+                    # leave on the chunk's stream while the next chunk's loop runs
                     sol_i = solver.solve(prob_i, dt0=dt0_i, args=args)
-                    ctx = dict(sol=sol_i)
+                    ctx = dict(sol=sol_i, copied=hi > lo)
+                    if hi > lo:
+                        for dst, src in ((ys, sol_i.ys), (status, sol_i.status), (n_steps, sol_i.stats["n_steps"]),
+                                         (n_accepted, sol_i.stats["n_accepted"]),
+                                         (n_init, sol_i.stats["n_initialized"])):
+                            dst[lo:hi].copy_(src, non_blocking=True)
                 else:
                     ctx = solver._fused_launch(prob_i, term_, field, dt0_i)
                     summaries[i].copy_(ctx["summary"], non_blocking=True)
@@ -103,11 +120,12 @@ def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, devic
                 else:
                     n_f_evals = max(n_f_evals, ctx["n_init_evals"] + ctx["n_stage_evals"] * iters)
             if sol_i is not None and hi > lo:
-                ys[lo:hi].copy_(sol_i.ys)
-                status[lo:hi].copy_(sol_i.status)
-                n_steps[lo:hi].copy_(sol_i.stats["n_steps"])
-                n_accepted[lo:hi].copy_(sol_i.stats["n_accepted"])
-                n_init[lo:hi].copy_(sol_i.stats["n_initialized"])
+                if not ctx.get("copied"):  # a replayed chunk: its results are final only now
+                    ys[lo:hi].copy_(sol_i.ys)
+                    status[lo:hi].copy_(sol_i.status)
+                    n_steps[lo:hi].copy_(sol_i.stats["n_steps"])
+                    n_accepted[lo:hi].copy_(sol_i.stats["n_accepted"])
+                    n_init[lo:hi].copy_(sol_i.stats["n_initialized"])
                 if "n_f_evals" in sol_i.stats:
                     n_f_evals = max(n_f_evals, int(sol_i.stats["n_f_evals"][0]))
     stats: Dict[str, Any] = {}
