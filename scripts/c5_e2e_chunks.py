@@ -1,5 +1,5 @@
 """configs[4] (64 rows x 2^20 grid values, 268 MB in and out) end to end from host buffers: solve_from_host with the
-batch cut into 1 / 2 / 4 / 8 chunks against copy-in, solve, copy-out in sequence."""
+batch cut into 1 / 2 / 4 / 8 chunks, driven by one or two host threads, against copy-in, solve, copy-out in sequence."""
 import statistics
 import sys
 import time
@@ -20,13 +20,15 @@ if te is not None and te.ndim == 1:
 hp = to.InitialValueProblem(host["y0"], host["t_start"], host["t_end"], te)
 moved = hp.y0.numel() * hp.y0.element_size() * 2
 with torch.no_grad():
-    for chunks in (1, 2, 4, 8):
-        out, times = None, []
-        for i in range(6):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            out = to.solve_from_host(solver, hp, "cuda", chunks=chunks, min_chunk_bytes=max(1, moved // chunks), out=out)
-            if i >= 2:
-                times.append(time.perf_counter() - t0)
-        print(f"chunks asked {chunks} run {solver.last_run['chunks']}: {statistics.median(times) * 1e3:.2f} ms "
-              f"(accepted {int(out.stats['n_accepted'].sum())})")
+    for workers in (1, 2):
+        for chunks in (1, 2, 4, 8):
+            out, times = None, []
+            for i in range(6):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                out = to.solve_from_host(solver, hp, "cuda", chunks=chunks, min_chunk_bytes=max(1, moved // chunks),
+                                         workers=workers, out=out)
+                if i >= 2:
+                    times.append(time.perf_counter() - t0)
+            print(f"host threads {workers}, chunks asked {chunks} run {solver.last_run['chunks']}: "
+                  f"{statistics.median(times) * 1e3:.2f} ms (accepted {int(out.stats['n_accepted'].sum())})")

@@ -26,18 +26,75 @@ def _pinned_like(shape, dtype) -> torch.Tensor:
     return torch.empty(shape, dtype=dtype, device="cpu", pin_memory=True)
 
 
+def _kernel_field(term_) -> bool:
+    """Fields of this package whose solve is host-driven but whose code is ours (safe to run from two threads)."""
+    from .fields import Heat1D, TanhMLP256
+
+    return isinstance(getattr(term_, "f", None), (Heat1D, TanhMLP256))
+
+
+def _solve_chunks_threaded(solver, staged, bounds, streams, device, args, workers, outs):
+    """Chunk i is solved by thread i % workers on stream i with that thread's own AutoDiffAdjoint (same step
+    method and controller objects -- they are immutable --, own plans / poll rings); results leave on the chunk's
+    stream.  ctypes and torch release the GIL around the calls that block."""
+    import threading
+
+    clones = solver.__dict__.setdefault("_host_workers", [])
+    while len(clones) < workers:
+        clones.append(AutoDiffAdjoint(solver.step_method, solver.step_size_controller))
+    for c in clones[:workers]:  # follow the caller's settings of this call
+        c.max_steps, c.lookahead = solver.max_steps, solver.lookahead
+        c.use_cuda_graph, c.use_step_fusion = solver.use_cuda_graph, solver.use_step_fusion
+        c.backprop_through_step_size_control = solver.backprop_through_step_size_control
+    pending: List[Optional[Dict[str, Any]]] = [None] * len(bounds)
+    errors: List[BaseException] = []
+
+    def work(tid):
+        try:
+            with torch.no_grad(), torch.cuda.device(device):
+                for i in range(tid, len(bounds), workers):
+                    lo, hi = bounds[i]
+                    prob_i, dt0_i = staged[i]
+                    with torch.cuda.stream(streams[i]):
+                        sol_i = clones[tid].solve(prob_i, dt0=dt0_i, args=args)
+                        if hi > lo:
+                            ys, status, n_steps, n_accepted, n_init = outs
+                            for dst, src in ((ys, sol_i.ys), (status, sol_i.status),
+                                             (n_steps, sol_i.stats["n_steps"]),
+                                             (n_accepted, sol_i.stats["n_accepted"]),
+                                             (n_init, sol_i.stats["n_initialized"])):
+                                dst[lo:hi].copy_(src, non_blocking=True)
+                    pending[i] = dict(sol=sol_i, copied=hi > lo, prob=prob_i, dt0=dt0_i)
+        except BaseException as e:  # re-raised by the caller's thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,), name=f"torchode_b200-host-{t}") for t in range(workers)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    solver.last_run = dict(clones[0].last_run)
+    return pending
+
+
 def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, device, *, chunks: int = 8,
-                    min_chunk: int = 4096, min_chunk_bytes: int = 256 << 20, dt0: Optional[torch.Tensor] = None,
-                    args: Any = None, out: Optional[Solution] = None) -> Solution:
+                    min_chunk: int = 4096, min_chunk_bytes: int = 128 << 20, workers: int = 2,
+                    dt0: Optional[torch.Tensor] = None, args: Any = None,
+                    out: Optional[Solution] = None) -> Solution:
     """``problem``: an InitialValueProblem over CPU tensors (pinned memory makes the copies
     asynchronous).  Returns a Solution over pinned CPU tensors.  ``out``: the Solution of an earlier
     call with the same shapes, whose buffers are reused (allocating pinned memory costs more than a
     solve).  A chunk is worth a stream of its own if it has ``min_chunk`` samples (small batches of narrow
     states are launch-bound: they run as one chunk) OR moves ``min_chunk_bytes`` over PCIe (few wide samples --
     64 x 4 MB rows of a method-of-lines grid -- are cut by bytes: their copies are what there is to hide).  The
-    default of 256 MB per chunk is what configs[4] measures (scripts/c5_e2e_chunks.py, 268 MB each way, B200):
-    22.2 ms in one piece, 20.8 ms in two, 22.4 in four, 27.2 in eight -- a chunk whose solve drives its loop from the
-    host pays that loop's latency again, which eats what the hidden copies give beyond two chunks."""
+    default of 128 MB per chunk is what configs[4] measures (scripts/c5_e2e_chunks.py, 268 MB each way, B200): one
+    host thread 22.0 ms in one piece, 20.7 in two chunks, 22.3 in four, 27.1 in eight -- a chunk whose solve drives
+    its loop from the host pays that loop's latency again; two host threads 20.2 / 19.6 / 22.9 ms in two / four /
+    eight chunks.
+    ``workers``: host threads driving such chunks (this package's kernel-backed fields only; a user's ``f`` is never
+    called from a second thread)."""
     device = torch.device(device)
     term_ = solver.step_method.term
     assert term_ is not None, "solve_from_host needs the ODE term on the step method"
@@ -81,7 +138,18 @@ def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, devic
                 t_eval = te_dev_row.expand(hi - lo, -1) if te_broadcast else to_dev(te_host, lo, hi)
                 staged.append((InitialValueProblem(to_dev(problem.y0, lo, hi), to_dev(problem.t_start, lo, hi),
                                                    to_dev(problem.t_end, lo, hi), t_eval), to_dev(dt0, lo, hi)))
+        if chunks > 1 and workers > 1 and _kernel_field(term_):
+            # the solve of a kernel-backed field drives its loop from the host (look-ahead launches, a polled control
+            # block, a few synchronisations around it): two host threads, each with a solver of its own over the
+            # same components, keep two chunks' loops going so that one chunk's host latency is the other's GPU time
+            pending = _solve_chunks_threaded(solver, staged, bounds, streams, device, args, workers,
+                                             (ys, status, n_steps, n_accepted, n_init))
+            staged_done = True
+        else:
+            staged_done = False
         for i, (lo, hi) in enumerate(bounds):
+            if staged_done:
+                break
             with torch.cuda.stream(streams[i]):
                 prob_i, dt0_i = staged[i]
                 field = solver._fused_eligible(prob_i, term_) if hi > lo else None
@@ -133,6 +201,6 @@ def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, devic
         stats["n_f_evals"] = torch.full((1,), n_f_evals, dtype=torch.long).expand(B)
     stats["n_steps"], stats["n_accepted"], stats["n_initialized"] = n_steps, n_accepted, n_init
     ts = problem.t_eval if problem.t_eval is not None else problem.t_end[:, None]
-    solver.last_run = {"route": "host-pipelined", "chunks": chunks,
+    solver.last_run = {"route": "host-pipelined", "chunks": chunks, "host_threads": workers if staged_done else 1,
                        "kernel_launches": 2 * chunks}
     return Solution(ts=ts, ys=ys, stats=stats, status=status)
