@@ -129,16 +129,27 @@ def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, devic
         te_dev_row = te_host[:1].to(device, non_blocking=True) if te_broadcast else None
         ready = torch.cuda.Event()
         ready.record()
-        # every chunk's copy-in is queued before the first solve: a chunk whose solve drives its loop from the
-        # host (opaque f, the kernel-backed fields) would otherwise hold back the copies of all later chunks
-        staged = []
-        for i, (lo, hi) in enumerate(bounds):
-            with torch.cuda.stream(streams[i]):
-                streams[i].wait_event(ready)
-                t_eval = te_dev_row.expand(hi - lo, -1) if te_broadcast else to_dev(te_host, lo, hi)
-                staged.append((InitialValueProblem(to_dev(problem.y0, lo, hi), to_dev(problem.t_start, lo, hi),
-                                                   to_dev(problem.t_end, lo, hi), t_eval), to_dev(dt0, lo, hi)))
-        if chunks > 1 and workers > 1 and _kernel_field(term_):
+        staged: List[Any] = [None] * chunks
+
+        def stage(i):
+            if staged[i] is None:
+                lo, hi = bounds[i]
+                with torch.cuda.stream(streams[i]):
+                    streams[i].wait_event(ready)
+                    t_eval = te_dev_row.expand(hi - lo, -1) if te_broadcast else to_dev(te_host, lo, hi)
+                    staged[i] = (InitialValueProblem(to_dev(problem.y0, lo, hi), to_dev(problem.t_start, lo, hi),
+                                                     to_dev(problem.t_end, lo, hi), t_eval), to_dev(dt0, lo, hi))
+            return staged[i]
+
+        # A chunk whose solve drives its loop from the host (opaque f, the kernel-backed fields) would hold back the
+        # copy-ins of all later chunks: those are queued before the first solve.  Whole-solve kernels are launched
+        # without a host synchronisation: their chunks keep copy-in, launch, copy-out interleaved in issue order
+        # (queueing eight chunks' copies first delays the first launch by ~0.3 ms of host time).
+        host_driven = B > 0 and solver._fused_eligible(stage(0)[0], term_) is None
+        if host_driven:
+            for i in range(chunks):
+                stage(i)
+        if host_driven and chunks > 1 and workers > 1 and _kernel_field(term_):
             # the solve of a kernel-backed field drives its loop from the host (look-ahead launches, a polled control
             # block, a few synchronisations around it): two host threads, each with a solver of its own over the
             # same components, keep two chunks' loops going so that one chunk's host latency is the other's GPU time
@@ -150,8 +161,8 @@ def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, devic
         for i, (lo, hi) in enumerate(bounds):
             if staged_done:
                 break
+            prob_i, dt0_i = stage(i)
             with torch.cuda.stream(streams[i]):
-                prob_i, dt0_i = staged[i]
                 field = solver._fused_eligible(prob_i, term_) if hi > lo else None
                 if field is None:
                     # opaque f / plug-ins / empty chunk: the solve synchronises with the host itself; its results
