@@ -260,8 +260,11 @@ __device__ __forceinline__ void epilogue_m64(uint32_t tmem_base, uint8_t* sA, ui
 //
 // Step-fused evaluation (tode_mlp_tanh256_step_forward, round 2): stages stage0 .. stage1 in ONE launch.  f acts
 // row by row, so a CTA's rows never need another CTA's results: the CTA forms y_i from the k_j it wrote itself a
-// stage earlier (global memory, L2-resident), evaluates the MLP, writes k_i and goes on -- no grid-wide
-// synchronisation, one launch + ramp-up instead of six, TMEM and barriers set up once.
+// stage earlier, evaluates the MLP, writes k_i and goes on -- no grid-wide synchronisation, one launch + ramp-up
+// instead of six, TMEM and barriers set up once.  With 64-row tiles (mlp_tanh256_kernel<64, true>) a stage does not
+// load its operands from global memory: the partial sum over all k_j but the newest is formed under the previous
+// stage's MMAs and kept in shared memory, the newest k_j is read from the staged output tile, y from TMEM (see the
+// comments in the kernel; DESIGN.md section 4 has the measurements).
 constexpr int kMaxStageK = 6;
 struct StageIn {
   float* k[kMaxStageK + 1];  // k[j], j < stage: operands; k[stage]: where stage `stage`'s f value goes
