@@ -312,3 +312,21 @@ def test_new_entry_points_report_argument_errors_without_a_gpu():
     B, F = 64, 1 << 20
     chunks_f32, chunks_f64 = F // 4096, F // 2048
     assert lib.tode_scratch_elems(B, F) >= 2 * B + 2 * B * max(chunks_f32, chunks_f64) + 8 * B
+
+
+def test_solve_from_host_chunk_count():
+    """host_pipeline.chunk_count: chunks are worth a stream by samples OR by bytes moved, never more than asked for
+    or than there are samples."""
+    from torchode_b200.host_pipeline import chunk_count
+
+    mb = 1 << 20
+    # configs[1]: 2^20 samples x 2 fp64, no t_eval: 32 MB moved, 256 chunks' worth of samples -> the 8 asked for
+    assert chunk_count(1 << 20, 2, 0, 8, 8, 4096, 128 * mb) == 8
+    # a small batch of narrow states is launch-bound: one chunk
+    assert chunk_count(1000, 2, 17, 4, 8, 4096, 128 * mb) == 1
+    # configs[4]: 64 rows x 2^20 fp32, 536 MB moved -> cut by bytes into 4
+    assert chunk_count(64, 1 << 20, 0, 4, 8, 4096, 128 * mb) == 4
+    assert chunk_count(64, 1 << 20, 0, 4, 2, 4096, 128 * mb) == 2  # never more than asked for
+    assert chunk_count(3, 1 << 26, 0, 4, 8, 4096, 128 * mb) == 3   # never more than samples
+    assert chunk_count(0, 2, 0, 8, 8, 4096, 128 * mb) == 1
+    assert chunk_count(12, 4096, 5, 4, 5, 4096, 64 << 10) == 5      # the explicit threshold of the GPU test

@@ -26,6 +26,16 @@ def _pinned_like(shape, dtype) -> torch.Tensor:
     return torch.empty(shape, dtype=dtype, device="cpu", pin_memory=True)
 
 
+def chunk_count(B: int, F: int, Tn: int, itemsize: int, chunks: int, min_chunk: int, min_chunk_bytes: int) -> int:
+    """How many chunks ``solve_from_host`` runs: at most ``chunks``, each worth a stream of its own either by samples
+    (``min_chunk``) or by bytes moved over PCIe (``min_chunk_bytes``: y0 in, ys out), never more than samples."""
+    if B <= 0:
+        return 1
+    moved = B * F * (1 + max(Tn, 1)) * itemsize
+    worth = max(B // max(1, int(min_chunk)), moved // max(1, int(min_chunk_bytes)))
+    return max(1, min(int(chunks), worth, B))
+
+
 def _kernel_field(term_) -> bool:
     """Fields of this package whose solve is host-driven but whose code is ours (safe to run from two threads)."""
     from .fields import Heat1D, TanhMLP256
@@ -100,9 +110,7 @@ def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, devic
     assert term_ is not None, "solve_from_host needs the ODE term on the step method"
     B, F, Tn = problem.batch_size, problem.n_features, problem.n_evaluation_points
     D = problem.data_dtype
-    moved = B * F * (1 + max(Tn, 1)) * torch.empty((), dtype=D).element_size()  # y0 in, ys out
-    worth = max(B // max(1, int(min_chunk)), moved // max(1, int(min_chunk_bytes)))
-    chunks = max(1, min(int(chunks), worth, B)) if B else 1
+    chunks = chunk_count(B, F, Tn, torch.empty((), dtype=D).element_size(), chunks, min_chunk, min_chunk_bytes)
     bounds = [shard_bounds(B, i, chunks) for i in range(chunks)]
     reuse = (out is not None and out.ys.shape == (B, max(Tn, 1), F) and out.ys.dtype == D
              and out.ys.is_pinned() and out.status.shape == (B,))
