@@ -72,6 +72,9 @@ class AutoDiffAdjoint(nn.Module):
         #: more (at capture): an opaque ``f`` must be capturable (no host sync, no data-dependent Python
         #: control flow) and must not count its calls or log on the host -- set ``True`` to opt in.
         self.use_cuda_graph: Optional[bool] = None
+        #: loop iterations recorded into one graph: a replay then costs one graph launch and one poll of the control
+        #: block per ``graph_iterations`` iterations (iterations after the stop flag are no-ops on the device)
+        self.graph_iterations = 4
         #: stage-wise route with the built-in ``fields.Heat1D`` as f and no ``t_eval``: run a whole loop
         #: iteration as ONE pass over y (stage values and the stencil's neighbours stay on chip,
         #: ``tode_heat_step``) instead of 6 x (stage kernel, f) + finish.  With ``fields.TanhMLP256`` as
@@ -303,6 +306,7 @@ class AutoDiffAdjoint(nn.Module):
         if use_graph and record is None:
             te = problem.t_eval
             key = (str(dev), B, F, Tn, D, Tt, general, step_fusion, stage_fusion, id(term_.f), id(args), dt0 is None,
+                   int(self.graph_iterations),
                    None if te is None else (te.stride(0) == 0), bytes(cab_t), bytes(cab_c))
             plan = self._plans.get(key)
             if plan is None:
@@ -429,18 +433,21 @@ class AutoDiffAdjoint(nn.Module):
             launch_iteration = launch_fused_iteration
         elif stage_fusion:
             launch_iteration = launch_mlp_iteration
-        launched = 0
+        launched = iters_launched = 0
         ctl_host = None
         graph = plan["graph"] if plan is not None else None
+        per_replay = max(1, int(self.graph_iterations))
         while True:
             if record is not None:
                 record.snapshot(st)
             if graph is not None:
                 graph.replay()
+                iters_launched += per_replay
             else:
                 launch_iteration(stream)
+                iters_launched += 1
                 if plan is not None and launched == 0:
-                    graph = self._capture_iteration(launch_iteration, dev)
+                    graph = self._capture_iteration(launch_iteration, dev, per_replay)
                     plan["graph"], plan["kp"], plan["ks"] = graph, kp, ks
             slot = launched % (look + 1)
             pinned[slot].copy_(st.ctl, non_blocking=True)
@@ -479,10 +486,10 @@ class AutoDiffAdjoint(nn.Module):
         route = "step-fused" if step_fusion else ("stage-fused" if stage_fusion else "staged")
         self.last_run = {"route": route + "+graph" if graph is not None else route, "iterations": iters,
                          "general": general,
-                         "iterations_launched": launched,
+                         "iterations_launched": iters_launched,
                          # 6 stage kernels + finish (3 launches in split mode) per launched iteration
                          # (step-fused heat route and MLP field with all stages in one launch: 2), + init
-                         "kernel_launches_min": launched * (2 if (step_fusion or (
+                         "kernel_launches_min": iters_launched * (2 if (step_fusion or (
                              stage_fusion and self.use_step_fusion != "stages")) else S) + (2 if dt0 is None else 1)}
         # speculative iterations after the stop flag are no-ops on the device
         if plain_term:
@@ -507,14 +514,15 @@ class AutoDiffAdjoint(nn.Module):
         return Solution(ts=ts, ys=ys, stats=stats, status=st.status.to(torch.long))
 
     @staticmethod
-    def _capture_iteration(launch_iteration, dev):
-        """Record one loop iteration into a CUDA graph: inside the capture torch's current stream
+    def _capture_iteration(launch_iteration, dev, repeat=1):
+        """Record ``repeat`` loop iterations into a CUDA graph: inside the capture torch's current stream
         is the capturing side stream, so the kernels launched through the C-ABI are handed that
         stream; f's outputs live in the graph's private memory pool (static addresses)."""
         graph = torch.cuda.CUDAGraph()
         torch.cuda.current_stream(dev).synchronize()
         with torch.cuda.graph(graph):
-            launch_iteration(_launch.stream_ptr(dev))
+            for _ in range(repeat):
+                launch_iteration(_launch.stream_ptr(dev))
         return graph
 
     # ------------------------------------------------------------------------------------
