@@ -36,11 +36,12 @@ def chunk_count(B: int, F: int, Tn: int, itemsize: int, chunks: int, min_chunk: 
     return max(1, min(int(chunks), worth, B))
 
 
-def _kernel_field(term_) -> bool:
-    """Fields of this package whose solve is host-driven but whose code is ours (safe to run from two threads)."""
-    from .fields import Heat1D, TanhMLP256
+def _kernel_field(solver, term_) -> bool:
+    """Fields of this package whose solve is host-driven, whose code is ours (safe to run from two threads) and whose
+    route records no CUDA graph (a capture in one thread does not tolerate allocations in another): Heat1D."""
+    from .fields import Heat1D
 
-    return isinstance(getattr(term_, "f", None), (Heat1D, TanhMLP256))
+    return isinstance(getattr(term_, "f", None), Heat1D) and not solver.use_cuda_graph
 
 
 def _solve_chunks_threaded(solver, staged, bounds, streams, device, args, workers, outs):
@@ -157,7 +158,7 @@ def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, devic
         if host_driven:
             for i in range(chunks):
                 stage(i)
-        if host_driven and chunks > 1 and workers > 1 and _kernel_field(term_):
+        if host_driven and chunks > 1 and workers > 1 and _kernel_field(solver, term_):
             # the solve of a kernel-backed field drives its loop from the host (look-ahead launches, a polled control
             # block, a few synchronisations around it): two host threads, each with a solver of its own over the
             # same components, keep two chunks' loops going so that one chunk's host latency is the other's GPU time
