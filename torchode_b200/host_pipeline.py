@@ -104,8 +104,8 @@ def solve_from_host(solver: AutoDiffAdjoint, problem: InitialValueProblem, devic
     host thread 22.0 ms in one piece, 20.7 in two chunks, 22.3 in four, 27.1 in eight -- a chunk whose solve drives
     its loop from the host pays that loop's latency again; two host threads 20.2 / 19.6 / 22.9 ms in two / four /
     eight chunks.
-    ``workers``: host threads driving such chunks (this package's kernel-backed fields only; a user's ``f`` is never
-    called from a second thread)."""
+    ``workers``: host threads driving such chunks (``fields.Heat1D`` only: this package's own code on a route that
+    records no CUDA graph; a user's ``f`` is never called from a second thread)."""
     device = torch.device(device)
     term_ = solver.step_method.term
     assert term_ is not None, "solve_from_host needs the ODE term on the step method"
